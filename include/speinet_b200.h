@@ -1,0 +1,130 @@
+/*
+ * speinet_b200.h -- C-ABI of the B200-native SearchTransfer hot path.
+ *
+ * Drop-in boundary for yangt1013/SPEINet (reference paths relative to /root/reference):
+ *   model/SearchTransfer.py:24-51   SearchTransfer.forward   -> spei_search_transfer
+ *   model/SearchTransfer.py:59-72   SelfTransfer search half -> spei_search_transfer with NULL pyramids
+ *   model/speinet.py:93-94,96-97,108-109  _decode fusion     -> spei_fuse_level
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes + a CUDA stream handle (void*, a cudaStream_t).  No torch types.
+ *   - every pointer is DEVICE memory owned by the caller; tensors are contiguous NCHW fp32 unless stated.
+ *   - the library never allocates persistent device memory, never frees caller memory and never
+ *     synchronises the device; all work is enqueued on `stream`.
+ *   - return value 0 = ok, negative = error (SPEI_ERR_*); spei_last_error() returns a thread-local message.
+ *   - sm_100a only.  There is no CPU path and no fallback: on any other device the calls fail.
+ */
+#ifndef SPEINET_B200_H_
+#define SPEINET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPEI_VERSION 100
+
+#define SPEI_OK 0
+#define SPEI_ERR_ARG (-1)        /* NULL pointer / bad shape / misaligned pointer            */
+#define SPEI_ERR_ARCH (-2)       /* current device is not compute capability 10.x            */
+#define SPEI_ERR_CUDA (-3)       /* a CUDA runtime / driver call failed                      */
+#define SPEI_ERR_WORKSPACE (-4)  /* workspace too small                                      */
+
+/* summation order + divisor of the overlap-add (SearchTransfer.py:44-46) */
+#define SPEI_FOLD_ORDER_CPU 1 /* bit 0: add in ascending (ki,kj) (torch CPU col2im) instead of ascending patch origin (CUDA col2im) */
+#define SPEI_FOLD_TRUE_DIV 2  /* bit 1: true division by 9 instead of x * (1.0f/9.0f)          */
+#define SPEI_FOLD_CUDA 0      /* what torch does on a CUDA device: CUDA col2im order, x*(1/9f) */
+#define SPEI_FOLD_CPU 3       /* what torch does on the CPU: CPU col2im order, x/9             */
+
+/* relevance engine */
+#define SPEI_SEARCH_TC 0    /* tcgen05 bf16 candidate pass + exact fp32 rescoring (default)  */
+#define SPEI_SEARCH_EXACT 1 /* fp32 CUDA-core exhaustive search (checker / debugging)        */
+
+/* Problem description.  The reference instantiates c3=128, c2=64, c1=32 (n_feat=32,
+ * speinet.py:53); lv2 / lv1 tensors are 2x / 4x the lv3 grids (SearchTransfer.py:36-38,44-46). */
+typedef struct SpeiShape {
+  int32_t n;         /* batch items (clips)                                                    */
+  int32_t h, w;      /* query grid  (lrsr_lv3 is [n, c3, h, w])                                 */
+  int32_t hr, wr;    /* reference grid per sharp frame (refsr_lv3 is [n, rf, c3, hr, wr])       */
+  int32_t rf;        /* sharp reference frames per item; 1 in the reference      */
+  int32_t c3, c2, c1;/* channels of lv3 / lv2 / lv1 (must be 128 / 64 / 32 in this version)    */
+  int32_t fold_mode; /* SPEI_FOLD_* (bit mask)                                                 */
+  int32_t search;    /* SPEI_SEARCH_*                                                          */
+  float eps;         /* candidate window of the bf16 pass in normalised relevance units; <=0 -> 2e-3 */
+} SpeiShape;
+
+/* Counters written by spei_search_transfer into caller memory (device, 4 x int32) when
+ * `stats` is non-NULL: [0] queries re-searched exhaustively in fp32 (candidate list saturated),
+ * [1] candidates rescored in fp32, [2..3] reserved. */
+
+int spei_version(void);
+const char *spei_last_error(void);
+
+/* Bytes of scratch the pipeline needs for `shape` (depends on the SM count of the current device). */
+int spei_workspace_bytes(const SpeiShape *shape, size_t *bytes);
+
+/*
+ * The whole of SearchTransfer.forward (SearchTransfer.py:24-51):
+ *   q      [n, c3, h, w]              lrsr_lv3
+ *   k      [n, rf, c3, hr, wr]        refsr_lv3 (one or more sharp frames)
+ *   ref1   [n, rf, c1, 4hr, 4wr]      ref_lv1   (may be NULL together with T1)
+ *   ref2   [n, rf, c2, 2hr, 2wr]      ref_lv2   (may be NULL together with T2)
+ *   ref3   [n, rf, c3, hr, wr]        ref_lv3   (may be NULL together with T3; may alias k)
+ *   S      [n, 1, h, w]   fp32        R_lv3_star viewed as a map           (:49)
+ *   T3/T2/T1 [n, c3, h, w] / [n, c2, 2h, 2w] / [n, c1, 4h, 4w]             (:44-46)
+ *   arg    [n, h*w] int64             R_lv3_star_arg, key index j = f*hr*wr + y*wr + x   (:34)  (may be NULL)
+ *   stats  4 x int32 device counters (may be NULL)
+ */
+int spei_search_transfer(const SpeiShape *shape, const float *q, const float *k, const float *ref1,
+                         const float *ref2, const float *ref3, float *S, float *T3, float *T2, float *T1,
+                         int64_t *arg, int32_t *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- individual stages (the pipeline above is exactly these, in this order) ---- */
+
+/* (a) unfold + normalize pre-pass (SearchTransfer.py:26-31) without materialising the unfolded
+ * tensors: stages q and k into the layouts the search kernels read and computes the per-patch
+ * reciprocal L2 norms.  Fills the staging part of `workspace`. */
+int spei_stage_norm(const SpeiShape *shape, const float *q, const float *k, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* (b) relevance bmm + max/argmax (SearchTransfer.py:33-34) on the staged operands.
+ * Writes S [n,1,h,w] and arg32 [n, h*w] int32 (and arg64 if non-NULL). */
+int spei_relevance_argmax(const SpeiShape *shape, float *S, int32_t *arg32, int64_t *arg64, int32_t *stats,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* (c) unfold(ref) + bis gather + fold + /9 of one pyramid level (SearchTransfer.py:36-46),
+ * level = 3, 2 or 1; ref is [n, rf, c, s*hr, s*wr], out is [n, c, s*h, s*w], s = 1, 2, 4.
+ * `arg32` is [n, h*w] int32 key indices (any values in [0, rf*hr*wr)). */
+int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, const float *ref, float *out,
+                     void *stream);
+
+/* (d) one fusion line of SPEINet._decode (speinet.py:93-94 / 96-97 / 108-109):
+ *   out = dec + (W . cat(dec, t) + b) * bicubic_up(S, scale),  scale in {1,2,4}
+ *   dec, t, out [n, c, scale*h, scale*w]; weight [c, 2c] (Conv2d 1x1 weight, speinet.py:55-57);
+ *   bias [c]; S [n, 1, h, w].  out may alias neither input. */
+int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const float *dec, const float *t,
+                    const float *S, const float *weight, const float *bias, float *out, void *stream);
+
+/* ---- diagnostics (used by tests and tools; not part of the reference-facing path) ---- */
+
+/* Runs the tcgen05 relevance kernel on the staged operands and additionally copies the raw fp32
+ * accumulator of (item 0, query tile 0, key tile 0) -- un-normalised bf16 dot products, row m =
+ * query m of the tile, column c = key c of the tile -- into acc_out [128][256] (device). */
+int spei_debug_relevance_tile(const SpeiShape *shape, float *acc_out, void *workspace, size_t workspace_bytes,
+                              void *stream);
+
+/* Copies the pipeline watchdog word of `workspace` to *host_out and synchronises `stream`.
+ * 0 = no barrier of the tcgen05 kernel timed out. */
+int spei_debug_error_flag(const SpeiShape *shape, void *workspace, size_t workspace_bytes, void *stream,
+                          int32_t *host_out);
+
+/* Tiling plan for `shape` on the current device, 16 x int32 (host):
+ * q.orient q.tu q.tv q.Upad q.Vpad  k.orient k.tu k.tv k.Ny k.Upad k.Vpad  QT KT G maxseg num_sms */
+int spei_plan_info(const SpeiShape *shape, int32_t *out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEINET_B200_H_ */

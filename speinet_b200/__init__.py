@@ -1,0 +1,13 @@
+"""speinet_b200: B200-native (sm_100a) SearchTransfer hot path of yangt1013/SPEINet.
+
+Only what the path needs: the CUDA kernels + C-ABI (`csrc/`, `include/speinet_b200.h`), and the
+host-side mirror of the reference interface (`SearchTransfer`, `SelfTransfer`, `fuse_level`,
+`install`).  No CPU path, no PyTorch fallback.
+"""
+from ._lib import LIB_PATH, load as load_library  # noqa: F401
+from .search_transfer import SearchTransfer, SelfTransfer, search_transfer  # noqa: F401
+from .fusion import fuse_level, decode_fused, install  # noqa: F401
+from .sharding import shard_clips, gather_outputs  # noqa: F401
+
+__all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "decode_fused", "install",
+           "shard_clips", "gather_outputs", "load_library", "LIB_PATH"]

@@ -1,0 +1,115 @@
+// Kernel (c): unfold(ref) -> bis gather -> fold -> /9 of one pyramid level
+// (/root/reference/model/SearchTransfer.py:36-46) in closed form:
+//
+//   T_s[n,c,y,x] = (1/9) * sum over the <=9 query cells q=(Y+dy, X+dx), Y=y/s, X=x/s, inside the HxW grid, of
+//                  ref_s[n, f(q), c, y + (hr(q)-(Y+dy))*s, x + (wr(q)-(X+dx))*s]     (0 outside the image)
+//
+// with (f, hr, wr) decoded from arg[n,q].  The 1.86 GB of unfolded + gathered patches the reference
+// materialises per 720p frame never exist.  One thread owns the s consecutive output pixels of one
+// query cell row (a float / float2 / float4), so every neighbour contribution is one aligned vector
+// load; a warp covers 32 consecutive cells = 32*s consecutive pixels, i.e. fully coalesced stores.
+// The <=9 terms are added in the order of torch's col2im so the result is bit-identical to
+// F.fold: ascending patch origin on CUDA (ATen/native/cuda/im2col.cuh:139-154), ascending (ki,kj)
+// on CPU (ATen/native/im2col.h:131-146); then x*(1/9f) resp. x/9 (hard part 4).
+#include "spei_common.cuh"
+
+namespace spei {
+
+template <int S> struct Vec;
+template <> struct Vec<1> { using T = float; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<4> { using T = float4; };
+
+__device__ __forceinline__ void vadd(float& a, const float& b) { a = __fadd_rn(a, b); }
+__device__ __forceinline__ void vadd(float2& a, const float2& b) { a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); }
+__device__ __forceinline__ void vadd(float4& a, const float4& b) {
+  a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+}
+template <bool kTrueDiv> __device__ __forceinline__ float ninth(float a) {
+  return kTrueDiv ? __fdiv_rn(a, 9.0f) : __fmul_rn(a, 1.0f / 9.0f);
+}
+template <bool D> __device__ __forceinline__ float fin(float a) { return ninth<D>(a); }
+template <bool D> __device__ __forceinline__ float2 fin(float2 a) { return make_float2(ninth<D>(a.x), ninth<D>(a.y)); }
+template <bool D> __device__ __forceinline__ float4 fin(float4 a) {
+  return make_float4(ninth<D>(a.x), ninth<D>(a.y), ninth<D>(a.z), ninth<D>(a.w));
+}
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// grid: (ceil(W/32), S*H, n)   block: (32 cells, 8 channel lanes)
+template <int S, bool kCpuOrder, bool kTrueDiv>
+__global__ void __launch_bounds__(256)
+gather_fold_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
+                   int H, int W, int Hr, int Wr) {
+  using V = typename Vec<S>::T;
+  const int X = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y, n = blockIdx.z;
+  if (X >= W) return;
+  const int Y = y / S;
+  const int lk1 = Hr * Wr, jmax = rf * lk1 - 1;
+  const size_t ref_plane = (size_t)(S * Hr) * (S * Wr);  // one channel of one reference frame
+  const int ref_pitch = S * Wr;
+
+  // decode the <=9 neighbours once; offsets are in floats relative to channel 0 of frame f
+  long long off[9];
+  unsigned valid = 0;
+  const int32_t* a = arg + (size_t)n * H * W;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    // CUDA col2im order: ascending (h_col, w_col); CPU order: ascending (ki,kj) = descending origin
+    const int tt = kCpuOrder ? 8 - t : t;
+    const int dy = tt / 3 - 1, dx = tt % 3 - 1;
+    const int qy = Y + dy, qx = X + dx;
+    off[t] = 0;
+    if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+      int j = __ldg(a + qy * W + qx);
+      j = min(max(j, 0), jmax);
+      const int f = j / lk1, rem = j - f * lk1;
+      const int hr = rem / Wr, wr = rem - hr * Wr;
+      const int cy = Y + hr - qy, cx = X + wr - qx;  // source cell
+      if (cy >= 0 && cy < Hr && cx >= 0 && cx < Wr) {
+        valid |= 1u << t;
+        off[t] = (long long)f * C * (long long)ref_plane + (long long)(cy * S + (y - Y * S)) * ref_pitch + (long long)cx * S;
+      }
+    }
+  }
+  const float* rbase = ref + (size_t)n * rf * C * ref_plane;
+  const size_t out_plane = (size_t)(S * H) * (S * W);
+  float* obase = out + (size_t)n * C * out_plane + (size_t)y * (S * W) + (size_t)X * S;
+  const int cpt = C / 8;
+  for (int ci = 0; ci < cpt; ++ci) {
+    const int c = threadIdx.y * cpt + ci;
+    const float* rc = rbase + (size_t)c * ref_plane;
+    V v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = (valid >> t) & 1u ? __ldg(reinterpret_cast<const V*>(rc + off[t])) : vzero(V{});
+    V acc = vzero(V{});
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      if ((valid >> t) & 1u) vadd(acc, v[t]);
+    *reinterpret_cast<V*>(obase + (size_t)c * out_plane) = fin<kTrueDiv>(acc);
+  }
+}
+
+int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
+                       const float* ref, float* out, cudaStream_t st) {
+  dim3 grid((w + 31) / 32, scale * h, n), block(32, 8);
+  if (c % 8) { set_error("gather_fold: channels must be a multiple of 8"); return SPEI_ERR_ARG; }
+#define GF(S_, O_, D_) gather_fold_kernel<S_, O_, D_><<<grid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
+#define GFS(S_)                                             \
+  do {                                                      \
+    if (cpu_order) { if (true_div) GF(S_, true, true); else GF(S_, true, false); }  \
+    else { if (true_div) GF(S_, false, true); else GF(S_, false, false); }          \
+  } while (0)
+  const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
+  if (scale == 1) GFS(1);
+  else if (scale == 2) GFS(2);
+  else GFS(4);
+#undef GFS
+#undef GF
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
+}
+
+}  // namespace spei

@@ -1,0 +1,77 @@
+// Shared host/device definitions for libspeinet_b200: tiling plan, workspace layout, error plumbing.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/speinet_b200.h"
+
+namespace spei {
+
+// ---- fixed geometry of the search -------------------------------------------------------------
+constexpr int kC3 = 128;          // lv3 channels (n_feat*4, speinet.py:53)
+constexpr int kCG = kC3 / 8;      // 16 channel groups of 8 bf16 = 16 bytes
+constexpr int kTileU = 8;         // tile extent along the fast (contiguous) image axis, both operands
+constexpr int kQTileV = 16;       // query tile: 8 x 16 positions = 128 MMA rows
+constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA columns
+constexpr int kTopK = 8;          // bf16-pass candidates kept per query per key segment
+constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
+constexpr int kStages = 6;        // key pipeline depth
+
+// One operand (query set or key set) staged in (u, v) coordinates: u is the fast axis in memory.
+// orient 0: u = x, v = y.   orient 1: u = y, v = x (image transposed so the tile grid wastes less).
+struct OperandPlan {
+  int orient;
+  int U, V;        // valid extent
+  int tile_v;      // tile height along v (16 for queries, Ny for keys)
+  int tu, tv;      // tiles along u / v
+  int Upad, Vpad;  // staged bf16 plane = [Vpad][Upad] pixels, 1-pixel zero border included
+  __host__ __device__ int tiles() const { return tu * tv; }
+};
+
+struct Plan {
+  int n, rf;
+  int H, W, Hr, Wr;
+  OperandPlan q, k;
+  int QT;          // query tiles per item
+  int KT;          // key tiles per item (all reference frames)
+  long long P;     // total (query tile, key tile) pairs = n*QT*KT
+  int G;           // persistent CTAs
+  int maxseg;      // max key segments a query tile is split into
+  // workspace offsets (bytes)
+  size_t off_qbf, off_kbf, off_q32, off_k32, off_rq, off_rk, off_rkpad, off_qss, off_kss;
+  size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag;
+  size_t total;
+};
+
+int make_plan(const SpeiShape& s, int num_sms, Plan* out);
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define SPEI_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return ::spei::cuda_fail(e__, #call); \
+  } while (0)
+
+// ---- stage launchers (defined in the .cu files) -----------------------------------------------
+int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st);
+int launch_relevance_tc(const Plan& p, char* ws, cudaStream_t st);
+void set_debug_acc(float* ptr);
+int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
+                   cudaStream_t st);
+int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, char* ws, cudaStream_t st);
+int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
+                       const int32_t* arg32, const float* ref, float* out, cudaStream_t st);
+int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
+                      const float* weight, const float* bias, float* out, cudaStream_t st);
+
+// position <-> index helpers shared by kernels
+__host__ __device__ inline int uv_to_linear(int orient, int u, int v, int W) {
+  return orient == 0 ? v * W + u : u * W + v;  // y*W + x
+}
+
+}  // namespace spei

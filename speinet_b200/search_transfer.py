@@ -1,0 +1,151 @@
+"""Drop-in `SearchTransfer` / `SelfTransfer` modules backed by libspeinet_b200 (sm_100a CUDA).
+
+Mirror of /root/reference/model/SearchTransfer.py: same constructor, same registered parameters
+(`search1`, `search2` -- state-dict keys survive a strict load), same `forward` signature
+`(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3)` and the same return tuple
+`(S, T_lv3, T_lv2, T_lv1)` (SearchTransfer.py:24,51; call site speinet.py:135).
+
+Host code is PyTorch only for device memory and streams; every arithmetic step runs in the
+hand-written kernels behind the C-ABI of include/speinet_b200.h.  There is no CPU path and no
+PyTorch fallback: CPU tensors, non-sm_100 devices or a missing library raise RuntimeError.
+The path is forward-only: inputs that require grad while grad mode is on raise instead of
+silently detaching (the reference is differentiable).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+TensorOrList = Union[torch.Tensor, Sequence[torch.Tensor]]
+_FOLD = {"cuda": _lib.FOLD_CUDA, "cpu": _lib.FOLD_CPU}
+_SEARCH = {"tc": _lib.SEARCH_TC, "exact": _lib.SEARCH_EXACT}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stack_frames(x: TensorOrList, name: str) -> torch.Tensor:
+    """[N,C,H,W] -> [N,1,C,H,W]; list of Rf such tensors or a 5-D tensor -> [N,Rf,C,H,W] (contiguous fp32)."""
+    if isinstance(x, (list, tuple)):
+        x = torch.stack([t.float() for t in x], dim=1)
+    elif x.dim() == 4:
+        x = x.unsqueeze(1)
+    elif x.dim() != 5:
+        raise RuntimeError(f"{name}: expected a 4-D tensor, a 5-D [N,Rf,C,H,W] tensor or a list of 4-D tensors")
+    return x.float().contiguous()
+
+
+def _check_inputs(tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("speinet_b200.SearchTransfer runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if torch.is_grad_enabled() and t.requires_grad:
+            raise RuntimeError("speinet_b200.SearchTransfer is forward-only: call it under torch.no_grad() "
+                               "or detach the inputs (the reference module is differentiable; this one is not)")
+
+
+def workspace_bytes(shape: _lib.SpeiShape) -> int:
+    n = ctypes.c_size_t(0)
+    _lib.check(_lib.load().spei_workspace_bytes(ctypes.byref(shape), ctypes.byref(n)), "spei_workspace_bytes")
+    return int(n.value)
+
+
+def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: TensorOrList = None,
+                    ref_lv2: TensorOrList = None, ref_lv3: TensorOrList = None, *, fold_mode: str = "cuda",
+                    search: str = "tc", eps: float = 0.0):
+    """Functional form.  Returns (S, T_lv3, T_lv2, T_lv1, arg[int64 N x L], stats[int32 x 4]).
+    Pyramid levels passed as None are skipped (their T is None)."""
+    lib = _lib.load()
+    out_dtype = lrsr_lv3.dtype
+    q = lrsr_lv3.float().contiguous()
+    k = _stack_frames(refsr_lv3, "refsr_lv3")
+    same3 = ref_lv3 is refsr_lv3
+    r3 = k if same3 else (_stack_frames(ref_lv3, "ref_lv3") if ref_lv3 is not None else None)
+    r2 = _stack_frames(ref_lv2, "ref_lv2") if ref_lv2 is not None else None
+    r1 = _stack_frames(ref_lv1, "ref_lv1") if ref_lv1 is not None else None
+    _check_inputs([t for t in (q, k, r1, r2, r3) if t is not None])
+    n, c3, h, w = q.shape
+    nk, rf, ck, hr, wr = k.shape
+    if nk != n or ck != c3:
+        raise RuntimeError(f"query {tuple(q.shape)} and reference {tuple(k.shape)} disagree in batch or channels")
+    for t, c, s, nm in ((r3, c3, 1, "ref_lv3"), (r2, c3 // 2, 2, "ref_lv2"), (r1, c3 // 4, 4, "ref_lv1")):
+        if t is not None and tuple(t.shape) != (n, rf, c, s * hr, s * wr):
+            raise RuntimeError(f"{nm}: expected {(n, rf, c, s * hr, s * wr)}, got {tuple(t.shape)}")
+    shape = _lib.SpeiShape(n=n, h=h, w=w, hr=hr, wr=wr, rf=rf, c3=c3, c2=c3 // 2, c1=c3 // 4,
+                           fold_mode=_FOLD[fold_mode], search=_SEARCH[search], eps=float(eps))
+    dev = q.device
+    with torch.cuda.device(dev):
+        ws_bytes = workspace_bytes(shape)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        S = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+        T3 = torch.empty((n, c3, h, w), dtype=torch.float32, device=dev) if r3 is not None else None
+        T2 = torch.empty((n, c3 // 2, 2 * h, 2 * w), dtype=torch.float32, device=dev) if r2 is not None else None
+        T1 = torch.empty((n, c3 // 4, 4 * h, 4 * w), dtype=torch.float32, device=dev) if r1 is not None else None
+        arg = torch.empty((n, h * w), dtype=torch.int64, device=dev)
+        stats = torch.empty(4, dtype=torch.int32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.spei_search_transfer(ctypes.byref(shape), _ptr(q), _ptr(k), _ptr(r1), _ptr(r2), _ptr(r3), _ptr(S),
+                                      _ptr(T3), _ptr(T2), _ptr(T1), _ptr(arg), _ptr(stats), ctypes.c_void_p(ws_ptr),
+                                      ctypes.c_size_t(ws_bytes), stream)
+        _lib.check(rc, "spei_search_transfer")
+        ws.record_stream(torch.cuda.current_stream(dev))
+    if out_dtype != torch.float32:  # bf16 / fp16 callers get their dtype back; arithmetic stayed fp32
+        S, T3, T2, T1 = (t.to(out_dtype) if t is not None else None for t in (S, T3, T2, T1))
+    return S, T3, T2, T1, arg, stats
+
+
+class SearchTransfer(nn.Module):
+    """Same surface as the reference class (SearchTransfer.py:7-51)."""
+
+    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tc", eps: float = 0.0):
+        super().__init__()
+        # never used in forward, exactly as in the reference (:10-11); kept for strict checkpoint loading
+        self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
+        self.search2 = nn.Conv2d(n_feat * 2, n_feat, kernel_size=1, stride=1, padding=0)
+        self.fold_mode, self.search, self.eps = fold_mode, search, eps
+        self.last_index = None   # R_lv3_star_arg of the last call, int64 [N, H*W]
+        self.last_stats = None   # int32 [4] device counters (see include/speinet_b200.h)
+
+    def bis(self, input, dim, index):
+        """Batch index select, kept for API compatibility (SearchTransfer.py:12-22):
+        out[n, ..., i, ...] = input[n, ..., index[n, i], ...] along `dim`."""
+        shape = [1] * input.dim()
+        shape[0], shape[dim] = input.size(0), -1
+        target = list(input.size())
+        target[dim] = index.size(1)
+        return torch.gather(input, dim, index.view(shape).expand(target))
+
+    def forward(self, lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, return_index: bool = False):
+        S, T3, T2, T1, arg, stats = search_transfer(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3,
+                                                     fold_mode=self.fold_mode, search=self.search, eps=self.eps)
+        self.last_index, self.last_stats = arg, stats
+        if return_index:
+            return S, T3, T2, T1, arg
+        return S, T3, T2, T1
+
+
+class SelfTransfer(nn.Module):
+    """Mirror of the reference SelfTransfer (SearchTransfer.py:53-79): the O(L^2) search runs in the
+    same kernels with keys = query transposed and flipped (:59) and no pyramid; the cheap
+    bicubic + 1x1-conv transfers (:70-76) stay PyTorch ops, as the scope table says."""
+
+    def __init__(self, n_feat: int = 32, search: str = "tc", eps: float = 0.0):
+        super().__init__()
+        self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
+        self.search2 = nn.Conv2d(n_feat * 2, n_feat, kernel_size=1, stride=1, padding=0)
+        self.search, self.eps = search, eps
+
+    def forward(self, lrsr_lv3):
+        keys = lrsr_lv3.transpose(2, 3).flip(2).contiguous()
+        S, _, _, _, _, _ = search_transfer(lrsr_lv3, keys, search=self.search, eps=self.eps)
+        T_lv2 = F.relu(self.search1(F.interpolate(lrsr_lv3, scale_factor=2, mode="bicubic")))
+        T_lv1 = F.relu(self.search2(F.interpolate(T_lv2, scale_factor=2, mode="bicubic")))
+        return S, lrsr_lv3, T_lv2, T_lv1

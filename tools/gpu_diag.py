@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""Stage-by-stage GPU diagnostics of the hot path (run on the B200 box; test infrastructure).
+
+    python tools/gpu_diag.py --stage env|fold|exact|tile|tc|fuse|time720 [--out gpurun_out/diag]
+
+Every stage prints a compact report and appends a JSON record to <out>_<stage>.json, so one
+`gpurun` call tells which layer of the pipeline is wrong.  Uses the oracle only as the checker.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from oracle.torch_port import search_transfer_torch, fuse_level_torch  # noqa: E402
+from speinet_b200 import _lib  # noqa: E402
+import _util as U  # noqa: E402
+
+REC = {}
+
+
+def golden(name):
+    with np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def stage_env():
+    REC["device"] = torch.cuda.get_device_name(0)
+    REC["cc"] = torch.cuda.get_device_capability(0)
+    REC["torch"] = torch.__version__
+    REC["lib_version"] = _lib.load().spei_version()
+    x = torch.randn(1 << 20, device="cuda")
+    REC["torch_cuda_div9_is_mul_recip"] = bool(torch.equal(x / (3. * 3.), x * torch.tensor(1.0 / 9.0, device="cuda")))
+    REC["torch_cuda_div9_is_true_div"] = bool(torch.equal(x / (3. * 3.), torch.from_numpy(x.cpu().numpy() / np.float32(9.0)).cuda()))
+    REC["plan_720p"] = U.plan_info(U.make_shape(1, 180, 320, 180, 320))
+    REC["plan_bsd_rf2"] = U.plan_info(U.make_shape(8, 120, 160, 120, 160, rf=2))
+    REC["plan_256"] = U.plan_info(U.make_shape(1, 64, 64, 64, 64))
+
+
+def stage_fold():
+    for name in ("st_same_grid", "st_ragged", "st_edge"):
+        g = golden(name)
+        n, _, h, w = g["q"].shape
+        hr, wr = g["ref_lv3"].shape[2:]
+        arg32 = cu(g["arg"].astype(np.int32))
+        res = {}
+        for lvl, key, gk in ((3, "ref_lv3", "T_lv3"), (2, "ref_lv2", "T_lv2"), (1, "ref_lv1", "T_lv1")):
+            ref = cu(g[key]).unsqueeze(1).contiguous()
+            out_cpu_mode = U.gather_fold(arg32, ref, lvl, n, h, w, hr, wr, 1, _lib.FOLD_CPU).cpu().numpy()
+            res[f"lv{lvl}_cpu_mode_bitexact_vs_reference_golden"] = bool(np.array_equal(out_cpu_mode, g[gk]))
+            # torch CUDA comparator: same ATen ops as the reference, on the GPU
+            _, T3, T2, T1, _ = search_transfer_torch_with_index(g, lvl)
+            want = {3: T3, 2: T2, 1: T1}[lvl]
+            for mode, nm in ((_lib.FOLD_CUDA, "cuda_order_mul"), (_lib.FOLD_TRUE_DIV, "cuda_order_truediv"),
+                             (_lib.FOLD_CPU, "cpu_order_truediv"), (_lib.FOLD_ORDER_CPU, "cpu_order_mul")):
+                got = U.gather_fold(arg32, ref, lvl, n, h, w, hr, wr, 1, mode)
+                res[f"lv{lvl}_{nm}_bitexact_vs_torch_cuda"] = bool(torch.equal(got, want))
+                if mode == _lib.FOLD_CUDA:
+                    res[f"lv{lvl}_maxabs_vs_torch_cuda"] = float((got - want).abs().max())
+        REC[name] = res
+
+
+def search_transfer_torch_with_index(g, lvl):
+    """torch CUDA fold path with the golden indices (so only gather/fold/div are compared)."""
+    import torch.nn.functional as F
+    idx = cu(g["arg"].astype(np.int64))
+    n, _, h, w = g["q"].shape
+    outs = {}
+    for level, key, p in ((3, "ref_lv3", dict(kernel_size=3, padding=1, stride=1)),
+                          (2, "ref_lv2", dict(kernel_size=6, padding=2, stride=2)),
+                          (1, "ref_lv1", dict(kernel_size=12, padding=4, stride=4))):
+        cols = F.unfold(cu(g[key]), **p)
+        picked = torch.gather(cols, 2, idx[:, None, :].expand(-1, cols.size(1), -1))
+        s = p["stride"]
+        outs[level] = F.fold(picked, output_size=(h * s, w * s), **p) / (3. * 3.)
+    return None, outs[3], outs[2], outs[1], idx
+
+
+def compare_search(name, q, k_list, S, arg32, ref_S, ref_arg):
+    agree, n_eq, n_tie = oracle.near_tie_agreement(q, k_list, arg32, ref_arg)
+    rel = np.abs(S - ref_S) / np.maximum(np.abs(ref_S), 1e-6)
+    return {"case": name, "queries": int(agree.size), "equal": n_eq, "near_tie": n_tie, "mismatch": int((~agree).sum()),
+            "S_max_rel_err": float(rel.max()), "S_max_abs_err": float(np.abs(S - ref_S).max())}
+
+
+def stage_search(search, label):
+    cases = []
+    for name in ("st_same_grid", "st_ragged", "st_edge"):
+        g = golden(name)
+        q, k = g["q"], g["ref_lv3"]
+        S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous(), search=search)
+        r = compare_search(name, q, k, S.cpu().numpy().reshape(q.shape[0], -1), arg32.cpu().numpy(), g["S"].reshape(q.shape[0], -1), g["arg"])
+        r.update(stats=stats.cpu().tolist(), error_flag=flag)
+        cases.append(r)
+        print(label, r, flush=True)
+    # medium random case against the numpy oracle, reference grid != query grid, two frames
+    rng = np.random.default_rng(5)
+    q = (rng.standard_normal((1, 128, 37, 50)) * 0.2).astype(np.float32)
+    ka = (rng.standard_normal((1, 128, 29, 44)) * 0.04).astype(np.float32)
+    kb = (rng.standard_normal((1, 128, 29, 44)) * 0.04).astype(np.float32)
+    qu = oracle.l2_normalize(oracle.unfold(q, 3, 1, 1), axis=1)
+    ku = oracle.l2_normalize(np.concatenate([oracle.unfold(ka, 3, 1, 1), oracle.unfold(kb, 3, 1, 1)], axis=2), axis=1)
+    ref_S, ref_arg = oracle.relevance(qu, ku)
+    S, arg32, stats, flag = U.run_search(cu(q), torch.stack([cu(ka), cu(kb)], dim=1).contiguous(), search=search)
+    r = compare_search("random_rf2_37x50_vs_29x44", q, [ka, kb], S.cpu().numpy().reshape(1, -1), arg32.cpu().numpy(), ref_S, ref_arg)
+    r.update(stats=stats.cpu().tolist(), error_flag=flag)
+    cases.append(r)
+    print(label, r, flush=True)
+    REC["cases"] = cases
+
+
+def stage_tile():
+    out = []
+    rng = np.random.default_rng(11)
+    for (h, w, hr, wr) in ((16, 8, 32, 8), (20, 24, 20, 24), (64, 64, 64, 64), (37, 50, 29, 44)):
+        q = (rng.standard_normal((1, 128, h, w))).astype(np.float32)
+        k = (rng.standard_normal((1, 128, hr, wr))).astype(np.float32)
+        acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous())
+        want = U.expected_debug_tile(q, k, info)
+        ncol = want.shape[1]
+        got = acc[:, :ncol].astype(np.float64)
+        err = np.abs(got - want)
+        r = {"shape": [h, w, hr, wr], "plan": info, "error_flag": flag, "max_abs_err": float(np.nanmax(err)),
+             "nan_count": int(np.isnan(got).sum()), "want_absmax": float(np.abs(want).max()),
+             "row_err": [float(np.nanmax(err[i])) for i in (0, 1, 7, 8, 9, 64, 127)],
+             "col_err": [float(np.nanmax(err[:, j])) for j in (0, 1, 7, 8, 9, ncol - 1)]}
+        if r["max_abs_err"] > 1e-2 * max(1.0, r["want_absmax"]):
+            # hints: is the result a permutation / transposition of the expectation?
+            gm, wm = np.nan_to_num(got), want
+            r["hint_corr_rows_sorted"] = float(np.abs(np.sort(gm, axis=None) - np.sort(wm, axis=None)).max())
+            r["hint_got_sample"] = gm[:2, :4].tolist()
+            r["hint_want_sample"] = wm[:2, :4].tolist()
+        out.append(r)
+        print("tile", r, flush=True)
+    REC["tiles"] = out
+
+
+def stage_fuse():
+    g = golden("fusion")
+    res = {}
+    from speinet_b200 import fuse_level
+    for lvl, scale in ((3, 1), (2, 2), (1, 4)):
+        f = fuse_level(cu(g[f"dec{lvl}"]), cu(g[f"t{lvl}"]), cu(g["S"]), cu(g[f"w{lvl}"]), cu(g[f"b{lvl}"]), scale).cpu().numpy()
+        want = g[f"f{lvl}"]
+        res[f"lv{lvl}_max_rel_err_vs_reference_golden"] = float((np.abs(f - want) / np.maximum(np.abs(want), 1e-3)).max())
+        ft = fuse_level_torch(cu(g[f"dec{lvl}"]), cu(g[f"t{lvl}"]), cu(g["S"]), cu(g[f"w{lvl}"]), cu(g[f"b{lvl}"]), scale).cpu().numpy()
+        res[f"lv{lvl}_max_abs_err_vs_torch_cuda"] = float(np.abs(f - ft).max())
+    REC["fusion"] = res
+
+
+def timed(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))[iters // 2]
+
+
+def stage_time720():
+    lib = _lib.load()
+    torch.manual_seed(0)
+    h, w = 180, 320
+    q = torch.randn(1, 128, h, w, device="cuda") * 0.2
+    k = (torch.randn(1, 1, 128, h, w, device="cuda") * 0.04).contiguous()
+    r2 = torch.randn(1, 1, 64, 2 * h, 2 * w, device="cuda") * 0.04
+    r1 = torch.randn(1, 1, 32, 4 * h, 4 * w, device="cuda") * 0.04
+    shape = U.make_shape(1, h, w, h, w)
+    ws, ptr, nbytes = U.alloc_workspace(shape)
+    S = torch.empty(1, 1, h, w, device="cuda")
+    arg32 = torch.empty(1, h * w, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    st = U.cur_stream()
+    wsp = ctypes.c_void_p(ptr)
+    REC["workspace_MB"] = nbytes / 1e6
+    t_stage = timed(lambda: _lib.check(lib.spei_stage_norm(ctypes.byref(shape), U.vp(q), U.vp(k), wsp, nbytes, st), "stage"))
+    t_rel = timed(lambda: _lib.check(lib.spei_relevance_argmax(ctypes.byref(shape), U.vp(S), U.vp(arg32), ctypes.c_void_p(0), U.vp(stats), wsp, nbytes, st), "rel"))
+    flag = ctypes.c_int32(0)
+    lib.spei_debug_error_flag(ctypes.byref(shape), wsp, nbytes, st, ctypes.byref(flag))
+    REC["error_flag"] = int(flag.value)
+    REC["stats"] = stats.cpu().tolist()
+    flops = 2.0 * (h * w) ** 2 * 1152
+    REC["ms_stage_norm"] = t_stage
+    REC["ms_relevance_plus_rescore"] = t_rel
+    REC["relevance_TFLOPs"] = flops / (t_rel * 1e-3) / 1e12
+    for lvl, ref in ((3, k), (2, r2), (1, r1)):
+        sc = {3: 1, 2: 2, 1: 4}[lvl]
+        out = torch.empty(1, ref.shape[2], sc * h, sc * w, device="cuda")
+        t = timed(lambda: _lib.check(lib.spei_gather_fold(ctypes.byref(shape), lvl, U.vp(arg32), U.vp(ref), U.vp(out), st), "gf"))
+        REC[f"ms_gather_fold_lv{lvl}"] = t
+        REC[f"GBs_gather_fold_lv{lvl}"] = 2 * out.numel() * 4 / (t * 1e-3) / 1e9
+    from speinet_b200 import fuse_level
+    for lvl, c, sc in ((3, 128, 1), (2, 64, 2), (1, 32, 4)):
+        dec = torch.randn(1, c, sc * h, sc * w, device="cuda")
+        tt = torch.randn(1, c, sc * h, sc * w, device="cuda")
+        wgt = torch.randn(c, 2 * c, 1, 1, device="cuda") * 0.05
+        b = torch.randn(c, device="cuda")
+        t = timed(lambda: fuse_level(dec, tt, S, wgt, b, sc))
+        REC[f"ms_fuse_lv{lvl}"] = t
+        REC[f"GBs_fuse_lv{lvl}"] = 3 * dec.numel() * 4 / (t * 1e-3) / 1e9
+    # self-consistency at full size: TC search vs exhaustive fp32 search on a query subset is too slow;
+    # instead check q == k => identity match (property test)
+    kq = k[:, 0].contiguous()
+    S2, a2, st2, fl2 = U.run_search(kq, k)
+    ident = torch.arange(h * w, device="cuda", dtype=torch.int32)[None]
+    REC["identity_match_frac"] = float((a2 == ident).float().mean())
+    REC["identity_S_min"] = float(S2.min())
+    REC["identity_stats"] = st2.cpu().tolist()
+    REC["identity_error_flag"] = fl2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", required=True)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag"))
+    a = ap.parse_args()
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    t0 = time.time()
+    fn = {"env": stage_env, "fold": stage_fold, "exact": lambda: stage_search(_lib.SEARCH_EXACT, "exact"),
+          "tc": lambda: stage_search(_lib.SEARCH_TC, "tc"), "tile": stage_tile, "fuse": stage_fuse,
+          "time720": stage_time720}[a.stage]
+    try:
+        fn()
+        REC["ok"] = True
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        REC["ok"] = False
+        REC["exception"] = "".join(traceback.format_exception_only(type(e), e))[-2000:]
+        traceback.print_exc()
+    REC["seconds"] = time.time() - t0
+    with open(f"{a.out}_{a.stage}.json", "w") as f:
+        json.dump(REC, f, indent=1, default=str)
+    print(json.dumps(REC, indent=1, default=str))
+
+
+if __name__ == "__main__":
+    main()
