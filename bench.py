@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the SearchTransfer hot path (BASELINE.json metric: 1280x720 frames/s; SearchTransfer
+% of tensor-core peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one 1280x720 GoPro-shaped clip's features per rank
+(BASELINE.json configs[1]): stage+norm -> tcgen05 relevance -> fp32 rescoring -> gather/fold x3 ->
+fusion x3.  `value` is whole-job frames/s with inputs resident in HBM; `e2e` is the same metric
+through the public module API (`speinet_b200.SearchTransfer` + `fuse_level`) with HOST buffers and the
+host<->device copies inside the timed region.  Multi-GPU: one process per GPU (torchrun), clips
+sharded by rank (weak scaling), one NCCL all-gather of a frame-shaped output per step.
+
+`--impl reference` times the reference's own CPU algorithm (oracle/torch_port.py: the same ATen
+operator sequence as model/SearchTransfer.py, which cannot travel to the GPU box) on the host cores,
+each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W, C3 = 180, 320, 128                      # lv3 grid of a 1280x720 frame (speinet.py:124-127)
+L = H * W
+FLOPS_RELEVANCE = 2.0 * L * L * 9 * C3        # 7.644 TFLOP
+KERNELS_PER_STEP = 2 + 3 + 1 + 4 + 3 + 3      # stage q, stage k, tcgen05, rescore group, gather/fold x3, fuse x3
+WORKLOAD = "searchtransfer_fusion_1280x720_1ref"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm on the host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float):
+    """Returns (frames_per_s, info).  Key-side preparation and the fold are timed once at full size;
+    each step times bmm + max on a slice of m query columns against all keys;
+    frame time = t_keys + t_query_side + t_gather + t_fold + (t_step / m) * L."""
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(1234)
+    q = torch.randn(1, C3, H, W, generator=g) * 0.2
+    lv3 = torch.randn(1, C3, H, W, generator=g) * 0.04
+    lv2 = torch.randn(1, C3 // 2, 2 * H, 2 * W, generator=g) * 0.04
+    lv1 = torch.randn(1, C3 // 4, 4 * H, 4 * W, generator=g) * 0.04
+    t0 = time.perf_counter()
+    keys, cols = tp.key_side(lv3, lv1, lv2, lv3)
+    t_keys = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    qcols = tp.query_side(q)
+    t_query = time.perf_counter() - t0
+    # calibrate the slice so that (steps + warmup) slices fit the budget
+    m = 64
+    t0 = time.perf_counter()
+    tp.search_slice(keys, qcols, 0, m)
+    t_cal = time.perf_counter() - t0
+    per_step = max(0.2, (budget_s - t_keys - t_query) / max(1, steps + warmup + 2))
+    m = int(max(64, min(L, m * per_step / max(t_cal, 1e-4) * 0.7)))
+    m = min(m, 4096)
+    times = []
+    arg_full = torch.zeros(1, L, dtype=torch.int64)
+    for i in range(warmup + steps):
+        lo = (i * m) % max(1, L - m)
+        t0 = time.perf_counter()
+        _, r_arg = tp.search_slice(keys, qcols, lo, lo + m)
+        dt = time.perf_counter() - t0
+        arg_full[:, lo:lo + m] = r_arg
+        if i >= warmup:
+            times.append(dt)
+    t0 = time.perf_counter()
+    picked = tp.gather_slice(cols, arg_full)
+    t_gather_full = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Ts = tp.fold_all(picked, H, W)
+    t_fold = time.perf_counter() - t0
+    del picked, cols, keys, qcols
+    # the three fusion lines of _decode (speinet.py:93-94, 96-97, 108-109), once at full size
+    torch.manual_seed(0)
+    S_map = torch.rand(1, 1, H, W, generator=g) * 0.2
+    t_fuse = 0.0
+    for lvl, sc in ((3, 1), (2, 2), (1, 4)):
+        c = Ts[lvl].shape[1]
+        conv = torch.nn.Conv2d(2 * c, c, 1)
+        dec = torch.randn(1, c, sc * H, sc * W, generator=g) * 0.3
+        t0 = time.perf_counter()
+        tp.fuse_level_torch(dec, Ts[lvl], S_map, conv.weight.detach(), conv.bias.detach(), sc)
+        t_fuse += time.perf_counter() - t0
+    t_step = statistics.median(times)
+    frame_s = t_keys + t_query + t_gather_full + t_fold + t_fuse + t_step / m * L
+    info = {"cores": cores, "slice_queries": m, "t_key_side_s": round(t_keys, 3), "t_query_side_s": round(t_query, 3),
+            "t_fold_s": round(t_fold, 3), "t_slice_s": round(t_step, 4), "t_gather_full_s": round(t_gather_full, 3),
+            "t_fusion_s": round(t_fuse, 3),
+            "frame_s_extrapolated": round(frame_s, 3),
+            "sample": (f"reference ATen op sequence (oracle/torch_port.py), fp32, {cores} threads: key-side unfold+normalize, query-side "
+                       f"unfold+normalize, gather x3 and fold x3 timed once at full 720p size; bmm+max timed per step on {m} of {L} query columns "
+                       f"against all {L} keys; frame time = fixed parts + slice time * {L}/{m}")}
+    return 1.0 / frame_s, info, t_step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fps, info, t_step = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": "searchtransfer_720p_frames_per_s", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["frame_s_extrapolated"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "query_grid": [H, W], "channels": C3, "clips_per_step_per_rank": 1},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "detail": info}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import speinet_b200
+    from speinet_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = speinet_b200.load_library()
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    mk = lambda *s, std=1.0: (torch.randn(*s, generator=gen) * std)
+    host = {"q": mk(1, C3, H, W, std=0.2), "lv3": mk(1, C3, H, W, std=0.04), "lv2": mk(1, C3 // 2, 2 * H, 2 * W, std=0.04),
+            "lv1": mk(1, C3 // 4, 4 * H, 4 * W, std=0.04), "dec3": mk(1, C3, H, W, std=0.3),
+            "dec2": mk(1, C3 // 2, 2 * H, 2 * W, std=0.3), "dec1": mk(1, C3 // 4, 4 * H, 4 * W, std=0.3)}
+    host = {k: v.pin_memory() for k, v in host.items()}
+    torch.manual_seed(0)
+    convs = {3: torch.nn.Conv2d(2 * C3, C3, 1), 2: torch.nn.Conv2d(C3, C3 // 2, 1), 1: torch.nn.Conv2d(C3 // 2, C3 // 4, 1)}
+    convs = {k: c.to(dev) for k, c in convs.items()}
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    k5 = d["lv3"].unsqueeze(1).contiguous()
+    r2, r1 = d["lv2"].unsqueeze(1).contiguous(), d["lv1"].unsqueeze(1).contiguous()
+    wts = {l: (c.weight.detach().reshape(c.weight.shape[0], -1).contiguous(), c.bias.detach().contiguous()) for l, c in convs.items()}
+
+    shape = _lib.SpeiShape(n=1, h=H, w=W, hr=H, wr=W, rf=1, c3=C3, c2=C3 // 2, c1=C3 // 4, fold_mode=_lib.FOLD_CUDA,
+                           search=_lib.SEARCH_TC, eps=0.0)
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.spei_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "workspace_bytes")
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+    wsp = ctypes.c_void_p((ws.data_ptr() + 255) // 256 * 256)
+    S = torch.empty(1, 1, H, W, device=dev)
+    arg32 = torch.empty(1, L, dtype=torch.int32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int32, device=dev)
+    T = {3: torch.empty(1, C3, H, W, device=dev), 2: torch.empty(1, C3 // 2, 2 * H, 2 * W, device=dev),
+         1: torch.empty(1, C3 // 4, 4 * H, 4 * W, device=dev)}
+    Fo = {l: torch.empty_like(T[l]) for l in T}
+    frame_out = torch.empty(world, 3, 4 * H, 4 * W, device=dev) if world > 1 else None
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sref = ctypes.byref(shape)
+    refs = {3: k5, 2: r2, 1: r1}
+    decs = {3: d["dec3"], 2: d["dec2"], 1: d["dec1"]}
+    scale = {3: 1, 2: 2, 1: 4}
+    chk = _lib.check
+
+    def step(ev=None):
+        chk(lib.spei_stage_norm(sref, vp(d["q"]), vp(k5), wsp, nbytes.value, stream), "stage_norm")
+        if ev:
+            ev[0].record()
+        chk(lib.spei_relevance_candidates(sref, wsp, nbytes.value, stream), "relevance_candidates")
+        if ev:
+            ev[1].record()
+        chk(lib.spei_rescore(sref, vp(S), vp(arg32), ctypes.c_void_p(0), vp(stats), wsp, nbytes.value, stream), "rescore")
+        for lvl in (3, 2, 1):
+            chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), stream), "gather_fold")
+        for lvl in (3, 2, 1):
+            c = T[lvl].shape[1]
+            chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
+                                    vp(Fo[lvl]), stream), "fuse_level")
+        if world > 1:  # gather a frame-shaped output across ranks (the path's only collective)
+            dist.all_gather_into_tensor(frame_out, Fo[1][:, :3].contiguous())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    tc_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(tc_ev[i])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    tc_ms = [a.elapsed_time(b) for a, b in tc_ev]
+
+    # ---- end to end through the public module API with host buffers ----
+    st_mod = speinet_b200.SearchTransfer().to(dev)
+    out_host = {l: torch.empty(Fo[l].shape, dtype=torch.float32).pin_memory() for l in Fo}
+    s_host = torch.empty(1, 1, H, W).pin_memory()
+    h2d = sum(host[k].numel() * 4 for k in host)
+    d2h = sum(v.numel() * 4 for v in out_host.values()) + s_host.numel() * 4
+
+    def e2e_step():
+        with torch.no_grad():
+            dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            Sx, T3, T2, T1 = st_mod(dd["q"], dd["lv3"], dd["lv1"], dd["lv2"], dd["lv3"])
+            f3 = speinet_b200.fuse_level(dd["dec3"], T3, Sx, convs[3].weight, convs[3].bias, 1)
+            f2 = speinet_b200.fuse_level(dd["dec2"], T2, Sx, convs[2].weight, convs[2].bias, 2)
+            f1 = speinet_b200.fuse_level(dd["dec1"], T1, Sx, convs[1].weight, convs[1].bias, 4)
+            out_host[3].copy_(f3, non_blocking=True); out_host[2].copy_(f2, non_blocking=True)
+            out_host[1].copy_(f1, non_blocking=True); s_host.copy_(Sx, non_blocking=True)
+            if world > 1:
+                dist.all_gather_into_tensor(frame_out, f1[:, :3].contiguous())
+        torch.cuda.synchronize(dev)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    peak_burst, peak_sus, hbm, which = peaks()
+    tc_avg_ms = statistics.mean(tc_ms)
+    achieved = FLOPS_RELEVANCE / (tc_avg_ms * 1e-3) / 1e12
+    line = {
+        "metric": "searchtransfer_720p_frames_per_s", "value": world * args.steps / (ms_total * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core candidates + f32 rescoring/fold/fusion",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "query_grid": [H, W], "ref_grid": [H, W], "ref_frames": 1, "channels": [C3, C3 // 2, C3 // 4],
+                   "clips_per_step_per_rank": 1, "l2": "inputs (443 MB per step) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"clips sharded over {world} rank(s), no data-path collective; one frame-shaped all-gather per step"
+                   if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "kernel": "relevance_tc_kernel", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                     "frac": achieved / peak_burst, "frac_of_sustained": achieved / peak_sus, "peak_source": which,
+                     "kernel_ms": tc_avg_ms, "kernel_share_of_step": tc_avg_ms / (ms_total / args.steps),
+                     "algorithmic_flops": FLOPS_RELEVANCE, "traffic": None},
+        "e2e": {"value": world * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "api": "speinet_b200.SearchTransfer + fuse_level, pinned host buffers, copies inside the timed region"},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "clocks": clocks,
+        "search_stats_last_step": stats.cpu().tolist(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fps, info, _ = cpu_reference_run(steps=4, warmup=1, budget_s=25.0)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                                "detail": {k: v for k, v in info.items() if k != "sample"}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

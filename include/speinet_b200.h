@@ -94,6 +94,13 @@ int spei_stage_norm(const SpeiShape *shape, const float *q, const float *k, void
 int spei_relevance_argmax(const SpeiShape *shape, float *S, int32_t *arg32, int64_t *arg64, int32_t *stats,
                           void *workspace, size_t workspace_bytes, void *stream);
 
+/* (b) split in its two halves, for callers that time or schedule them separately:
+ *   spei_relevance_candidates : the tcgen05 bf16 pass; leaves per-query candidate lists in `workspace`
+ *   spei_rescore              : exact fp32 rescoring + tie-break + exhaustive fallback -> S, arg32 (, arg64) */
+int spei_relevance_candidates(const SpeiShape *shape, void *workspace, size_t workspace_bytes, void *stream);
+int spei_rescore(const SpeiShape *shape, float *S, int32_t *arg32, int64_t *arg64, int32_t *stats, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
 /* (c) unfold(ref) + bis gather + fold + /9 of one pyramid level (SearchTransfer.py:36-46),
  * level = 3, 2 or 1; ref is [n, rf, c, s*hr, s*wr], out is [n, c, s*h, s*w], s = 1, 2, 4.
  * `arg32` is [n, h*w] int32 key indices (any values in [0, rf*hr*wr)). */

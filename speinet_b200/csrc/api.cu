@@ -178,6 +178,24 @@ int spei_stage_norm(const SpeiShape* shape, const float* q, const float* k, void
   return launch_stage_norm(p, q, k, (char*)workspace, (cudaStream_t)stream);
 }
 
+int spei_relevance_candidates(const SpeiShape* shape, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan p;
+  int rc = prepare(shape, workspace, workspace_bytes, &p);
+  if (rc) return rc;
+  return launch_relevance_tc(p, (char*)workspace, (cudaStream_t)stream);
+}
+
+int spei_rescore(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  Plan p;
+  int rc = prepare(shape, workspace, workspace_bytes, &p);
+  if (rc) return rc;
+  if ((rc = check_ptr(S, "S", 4)) || (rc = check_ptr(arg32, "arg32", 4))) return rc;
+  if (stats) SPEI_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));
+  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  return launch_rescore(p, eps, S, arg32, arg64, stats, (char*)workspace, (cudaStream_t)stream);
+}
+
 int spei_relevance_argmax(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats,
                           void* workspace, size_t workspace_bytes, void* stream) {
   Plan p;

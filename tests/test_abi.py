@@ -1,0 +1,69 @@
+"""C-ABI boundary checks that need no GPU: the library loads, exports every symbol that
+include/speinet_b200.h declares, and the ctypes table mirrors the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "speinet_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from speinet_b200 import build, _lib
+    build.build()          # no-op when up to date; nvcc cross-compiles sm_100a without a GPU
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spei_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for must in ("spei_search_transfer", "spei_stage_norm", "spei_relevance_argmax", "spei_gather_fold",
+                 "spei_fuse_level", "spei_workspace_bytes", "spei_last_error", "spei_version"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/speinet_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib):
+    from speinet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert ctypes.sizeof(_lib.SpeiShape) == 12 * 4
+
+
+def test_version_and_error_string(lib):
+    text = open(HEADER).read()
+    assert lib.spei_version() == int(re.search(r"#define SPEI_VERSION (\d+)", text).group(1))
+    assert isinstance(lib.spei_last_error(), bytes)
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    from speinet_b200 import _lib
+    bad = _lib.SpeiShape(n=0, h=4, w=4, hr=4, wr=4, rf=1, c3=128, c2=64, c1=32)
+    n = ctypes.c_size_t(0)
+    assert lib.spei_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1
+    assert b"dimension" in lib.spei_last_error()
+    bad = _lib.SpeiShape(n=1, h=4, w=4, hr=4, wr=4, rf=1, c3=64, c2=32, c1=16)
+    assert lib.spei_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1
+    assert b"channels" in lib.spei_last_error()
+
+
+def test_no_silent_fallback_without_gpu(lib):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from speinet_b200 import _lib
+    ok = _lib.SpeiShape(n=1, h=8, w=8, hr=8, wr=8, rf=1, c3=128, c2=64, c1=32)
+    n = ctypes.c_size_t(0)
+    assert lib.spei_workspace_bytes(ctypes.byref(ok), ctypes.byref(n)) < 0

@@ -1,0 +1,352 @@
+"""Parity of the CUDA hot path against the oracle, through the C-ABI / the drop-in module.
+Run on the B200 box: python -m pytest tests -m gpu.
+
+Bars (BASELINE.json north_star): argmax indices bit-exact except near-ties with
+|delta relevance| < 1e-5 (fp32 normalisation, fp64 dot); given identical indices gather/fold is
+bit-exact; R_star (S) and fused features within 1e-4 relative in fp32, 1e-2 for bf16 inputs.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.torch_port import search_transfer_torch, fuse_level_torch
+from speinet_b200 import _lib
+import speinet_b200
+import _util as U
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = ["st_same_grid", "st_ragged", "st_edge"]
+RTOL_S = 1e-4
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_indices_agree(q, k_list, got, want):
+    agree, n_eq, n_tie = oracle.near_tie_agreement(q, k_list, got, want)
+    assert agree.all(), f"{int((~agree).sum())} of {agree.size} argmax indices differ beyond the 1e-5 near-tie rule"
+    return n_tie
+
+
+def test_library_is_the_native_one():
+    lib = speinet_b200.load_library()
+    assert lib.spei_version() == 100
+    info = U.plan_info(U.make_shape(1, 180, 320, 180, 320))
+    assert info["num_sms"] >= 100 and info["G"] == info["num_sms"]
+
+
+def test_torch_cuda_divides_by_multiplying_reciprocal():
+    """SURVEY section 7 hard part 4: pins the SPEI_FOLD_CUDA default."""
+    x = torch.randn(1 << 16, device="cuda")
+    assert torch.equal(x / (3. * 3.), x * torch.tensor(1.0 / 9.0, device="cuda"))
+
+
+# ------------------------------------------------------------------ (a)+(b) search ---------------
+@pytest.mark.parametrize("search", ["tc", "exact"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_search_matches_reference_golden(golden, name, search):
+    g = golden(name)
+    q, k = g["q"], g["ref_lv3"]
+    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous(),
+                                         search=_lib.SEARCH_TC if search == "tc" else _lib.SEARCH_EXACT)
+    assert flag == 0
+    assert_indices_agree(q, k, arg32.cpu().numpy(), g["arg"])
+    np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
+
+
+def test_edge_semantics_zero_patch_and_duplicate_keys(golden):
+    g = golden("st_edge")
+    S, arg32, _, _ = U.run_search(cu(g["q"]), cu(g["ref_lv3"]).unsqueeze(1).contiguous())
+    arg = arg32.cpu().numpy().reshape(8, 16)
+    S = S.cpu().numpy()[0, 0]
+    assert (arg[0:2, 0:2] == 0).all() and (S[0:2, 0:2] == 0).all()      # zero query patch -> index 0, S = 0
+    assert np.array_equal(arg[4:, 9:15], arg[4:, 1:7]) and (arg[:, 9:15] % 16 < 8).all()  # first duplicate wins
+    assert np.array_equal(arg, g["arg"].reshape(8, 16))
+
+
+@pytest.mark.parametrize("shape", [(1, 37, 50, 29, 44, 1), (2, 24, 40, 24, 40, 1), (1, 33, 21, 40, 35, 2), (1, 64, 64, 64, 64, 1)])
+def test_tc_search_matches_oracle_random(shape):
+    n, h, w, hr, wr, rf = shape
+    rng = np.random.default_rng(hash(shape) % (1 << 31))
+    q = (rng.standard_normal((n, 128, h, w)) * 0.2).astype(np.float32)
+    ks = [(rng.standard_normal((n, 128, hr, wr)) * 0.04).astype(np.float32) for _ in range(rf)]
+    qu = oracle.l2_normalize(oracle.unfold(q, 3, 1, 1), axis=1)
+    ku = oracle.l2_normalize(np.concatenate([oracle.unfold(k, 3, 1, 1) for k in ks], axis=2), axis=1)
+    want_S, want_arg = oracle.relevance(qu, ku)
+    S, arg32, stats, flag = U.run_search(cu(q), torch.stack([cu(k) for k in ks], dim=1).contiguous())
+    assert flag == 0
+    assert_indices_agree(q, ks, arg32.cpu().numpy(), want_arg)
+    np.testing.assert_allclose(S.cpu().numpy().reshape(n, -1), want_S, rtol=RTOL_S, atol=1e-6)
+
+
+def test_tc_search_smooth_features_many_near_candidates():
+    """Image-like (spatially smooth) features put many keys inside the candidate window; the
+    saturated-list -> exhaustive fp32 fallback must keep the result exact."""
+    rng = np.random.default_rng(9)
+    base = rng.standard_normal((1, 128, 10, 12)).astype(np.float32)
+    up = torch.nn.functional.interpolate(torch.from_numpy(base), scale_factor=4, mode="bicubic").numpy()
+    q = (up + 0.01 * rng.standard_normal(up.shape)).astype(np.float32)
+    k = (up + 0.01 * rng.standard_normal(up.shape)).astype(np.float32)
+    qu = oracle.l2_normalize(oracle.unfold(q, 3, 1, 1), axis=1)
+    ku = oracle.l2_normalize(oracle.unfold(k, 3, 1, 1), axis=1)
+    want_S, want_arg = oracle.relevance(qu, ku)
+    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous())
+    assert flag == 0
+    assert_indices_agree(q, k, arg32.cpu().numpy(), want_arg)
+    np.testing.assert_allclose(S.cpu().numpy().reshape(1, -1), want_S, rtol=RTOL_S, atol=1e-6)
+
+
+def test_debug_tile_accumulator_matches_bf16_dot():
+    """The raw tcgen05 accumulator of (query tile 0, key tile 0) equals the bf16-operand dot products."""
+    rng = np.random.default_rng(1)
+    q = rng.standard_normal((1, 128, 20, 24)).astype(np.float32)
+    k = rng.standard_normal((1, 128, 20, 24)).astype(np.float32)
+    acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous())
+    want = U.expected_debug_tile(q, k, info)
+    assert flag == 0
+    np.testing.assert_allclose(acc[:, :want.shape[1]], want, rtol=0, atol=2e-3)
+
+
+# ------------------------------------------------------------------ (c) gather / fold -----------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gather_fold_bit_exact_given_reference_indices(golden, name):
+    g = golden(name)
+    n, _, h, w = g["q"].shape
+    hr, wr = g["ref_lv3"].shape[2:]
+    arg32 = cu(g["arg"].astype(np.int32))
+    idx64 = cu(g["arg"].astype(np.int64))
+    # torch CUDA runs the same ATen ops as the reference: the bit-exact comparator for the default mode
+    tq = cu(g["q"])
+    for lvl, key, gk in ((3, "ref_lv3", "T_lv3"), (2, "ref_lv2", "T_lv2"), (1, "ref_lv1", "T_lv1")):
+        ref = cu(g[key]).unsqueeze(1).contiguous()
+        got_cpu_mode = U.gather_fold(arg32, ref, lvl, n, h, w, hr, wr, 1, _lib.FOLD_CPU)
+        assert np.array_equal(got_cpu_mode.cpu().numpy(), g[gk]), f"lv{lvl}: CPU-order fold differs from the reference golden"
+        p = {3: dict(kernel_size=3, padding=1, stride=1), 2: dict(kernel_size=6, padding=2, stride=2),
+             1: dict(kernel_size=12, padding=4, stride=4)}[lvl]
+        cols = torch.nn.functional.unfold(cu(g[key]), **p)
+        picked = torch.gather(cols, 2, idx64[:, None, :].expand(-1, cols.size(1), -1))
+        s = p["stride"]
+        want = torch.nn.functional.fold(picked, output_size=(h * s, w * s), **p) / (3. * 3.)
+        got = U.gather_fold(arg32, ref, lvl, n, h, w, hr, wr, 1, _lib.FOLD_CUDA)
+        assert torch.equal(got, want), f"lv{lvl}: CUDA-order fold differs from torch CUDA F.fold"
+
+
+def test_gather_fold_multi_frame_and_oracle_closed_form():
+    rng = np.random.default_rng(4)
+    n, h, w, hr, wr, rf = 2, 11, 13, 9, 17, 2
+    arg = rng.integers(0, rf * hr * wr, size=(n, h * w)).astype(np.int32)
+    for lvl, c, s in ((3, 128, 1), (2, 64, 2), (1, 32, 4)):
+        refs = [rng.standard_normal((n, c, s * hr, s * wr)).astype(np.float32) for _ in range(rf)]
+        want = oracle.closed_form_transfer(arg, refs, s, h, w, fold_order="cuda", div_mode="cuda")
+        ref = torch.stack([cu(r) for r in refs], dim=1).contiguous()
+        got = U.gather_fold(cu(arg), ref, lvl, n, h, w, hr, wr, rf, _lib.FOLD_CUDA)
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------ whole module ---------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_module_matches_reference_golden(golden, name):
+    g = golden(name)
+    st = speinet_b200.SearchTransfer(fold_mode="cpu").cuda()
+    k = cu(g["ref_lv3"])
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(cu(g["q"]), k, cu(g["ref_lv1"]), cu(g["ref_lv2"]), k, return_index=True)
+    n_tie = assert_indices_agree(g["q"], g["ref_lv3"], arg.cpu().numpy(), g["arg"])
+    np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
+    assert S.shape == g["S"].shape and S.dtype == torch.float32 and arg.dtype == torch.int64
+    if n_tie == 0:
+        assert np.array_equal(T3.cpu().numpy(), g["T_lv3"])
+        assert np.array_equal(T2.cpu().numpy(), g["T_lv2"])
+        assert np.array_equal(T1.cpu().numpy(), g["T_lv1"])
+
+
+def test_module_vs_torch_cuda_reference_ops_medium():
+    """Against the torch-CUDA restatement (same ATen ops as the reference) at a mid size."""
+    torch.manual_seed(3)
+    n, h, w = 2, 45, 80
+    q = torch.randn(n, 128, h, w, device="cuda") * 0.2
+    lv3 = torch.randn(n, 128, h, w, device="cuda") * 0.04
+    lv2 = torch.randn(n, 64, 2 * h, 2 * w, device="cuda") * 0.04
+    lv1 = torch.randn(n, 32, 4 * h, 4 * w, device="cuda") * 0.04
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        wS, w3, w2, w1, warg = search_transfer_torch_cuda(q, lv3, lv1, lv2, lv3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(q, lv3, lv1, lv2, lv3, return_index=True)
+    n_tie = assert_indices_agree(q.cpu().numpy(), lv3.cpu().numpy(), arg.cpu().numpy(), warg.cpu().numpy())
+    torch.testing.assert_close(S, wS, rtol=RTOL_S, atol=1e-6)
+    same = (arg == warg)
+    if bool(same.all()):
+        assert torch.equal(T3, w3) and torch.equal(T2, w2) and torch.equal(T1, w1)
+
+
+def search_transfer_torch_cuda(q, lv3, lv1, lv2, ref3):
+    import torch.nn.functional as F
+    n, _, h, w = q.shape
+    keys = F.normalize(F.unfold(lv3, 3, padding=1).permute(0, 2, 1), dim=2)
+    qc = F.normalize(F.unfold(q, 3, padding=1), dim=1)
+    r_star, r_arg = torch.max(torch.bmm(keys, qc), dim=1)
+    outs = {}
+    for lvl, ref, p in ((3, ref3, dict(kernel_size=3, padding=1, stride=1)), (2, lv2, dict(kernel_size=6, padding=2, stride=2)),
+                        (1, lv1, dict(kernel_size=12, padding=4, stride=4))):
+        cols = F.unfold(ref, **p)
+        picked = torch.gather(cols, 2, r_arg[:, None, :].expand(-1, cols.size(1), -1))
+        s = p["stride"]
+        outs[lvl] = F.fold(picked, output_size=(h * s, w * s), **p) / (3. * 3.)
+    return r_star.view(n, 1, h, w), outs[3], outs[2], outs[1], r_arg
+
+
+def test_two_reference_frames_extension():
+    rng = np.random.default_rng(12)
+    n, h, w = 1, 14, 18
+    q = (rng.standard_normal((n, 128, h, w)) * 0.2).astype(np.float32)
+    pyr = lambda: ((rng.standard_normal((n, 32, 4 * h, 4 * w)) * 0.04).astype(np.float32),
+                   (rng.standard_normal((n, 64, 2 * h, 2 * w)) * 0.04).astype(np.float32),
+                   (rng.standard_normal((n, 128, h, w)) * 0.04).astype(np.float32))
+    a1, a2, a3 = pyr()
+    b1, b2, b3 = pyr()
+    wS, w3, w2, w1, warg, _ = oracle.search_transfer(q, [a3, b3], [a1, b1], [a2, b2], [a3, b3], fold_order="cuda", div_mode="cuda")
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(cu(q), [cu(a3), cu(b3)], [cu(a1), cu(b1)], [cu(a2), cu(b2)], [cu(a3), cu(b3)], return_index=True)
+    n_tie = assert_indices_agree(q, [a3, b3], arg.cpu().numpy(), warg)
+    np.testing.assert_allclose(S.cpu().numpy(), wS, rtol=RTOL_S, atol=1e-6)
+    assert (arg >= h * w).any() and (arg < h * w).any()  # both frames win somewhere
+    if n_tie == 0:
+        assert np.array_equal(T1.cpu().numpy(), w1) and np.array_equal(T2.cpu().numpy(), w2) and np.array_equal(T3.cpu().numpy(), w3)
+
+
+def test_bf16_inputs_within_1e2():
+    rng = np.random.default_rng(21)
+    h, w = 16, 24
+    q = cu((rng.standard_normal((1, 128, h, w)) * 0.2).astype(np.float32)).bfloat16()
+    lv3 = cu((rng.standard_normal((1, 128, h, w)) * 0.04).astype(np.float32)).bfloat16()
+    lv2 = cu((rng.standard_normal((1, 64, 2 * h, 2 * w)) * 0.04).astype(np.float32)).bfloat16()
+    lv1 = cu((rng.standard_normal((1, 32, 4 * h, 4 * w)) * 0.04).astype(np.float32)).bfloat16()
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1 = st(q, lv3, lv1, lv2, lv3)
+    assert S.dtype == torch.bfloat16 and T1.dtype == torch.bfloat16
+    # oracle for bf16 = fp32 reference on the bf16 inputs upcast to fp32
+    f = lambda t: t.float().cpu().numpy()
+    wS, w3, w2, w1, _, _ = oracle.search_transfer(f(q), f(lv3), f(lv1), f(lv2), f(lv3), fold_order="cuda", div_mode="cuda")
+    np.testing.assert_allclose(f(S), wS, rtol=1e-2, atol=1e-3)
+    np.testing.assert_allclose(f(T1), w1, rtol=1e-2, atol=1e-3)
+    np.testing.assert_allclose(f(T3), w3, rtol=1e-2, atol=1e-3)
+
+
+def test_self_transfer_search(golden):
+    g = golden("self_transfer")
+    m = speinet_b200.SelfTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1 = m(cu(g["q"]))
+    np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
+    assert T3.shape == g["q"].shape and T2.shape == (1, 64, 16, 24) and T1.shape == (1, 32, 32, 48)
+
+
+# ------------------------------------------------------------------ (d) fusion ------------------
+def test_fusion_matches_reference_golden(golden):
+    g = golden("fusion")
+    for lvl, scale in ((3, 1), (2, 2), (1, 4)):
+        f = speinet_b200.fuse_level(cu(g[f"dec{lvl}"]), cu(g[f"t{lvl}"]), cu(g["S"]), cu(g[f"w{lvl}"]), cu(g[f"b{lvl}"]), scale)
+        np.testing.assert_allclose(f.cpu().numpy(), g[f"f{lvl}"], rtol=1e-4, atol=1e-6)
+
+
+def test_fusion_odd_sizes_vs_oracle():
+    rng = np.random.default_rng(8)
+    h, w = 7, 9  # plane not a multiple of 4 or of the 128-pixel tile
+    S = (rng.random((2, 1, h, w)) * 0.2).astype(np.float32)
+    for c, scale in ((128, 1), (64, 2), (32, 4)):
+        dec = rng.standard_normal((2, c, h * scale, w * scale)).astype(np.float32)
+        t = rng.standard_normal((2, c, h * scale, w * scale)).astype(np.float32)
+        wt = (rng.standard_normal((c, 2 * c, 1, 1)) * 0.05).astype(np.float32)
+        b = rng.standard_normal(c).astype(np.float32)
+        got = speinet_b200.fuse_level(cu(dec), cu(t), cu(S), cu(wt), cu(b), scale).cpu().numpy()
+        want = oracle.fuse_level(dec, t, S, wt, b, scale)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ full size properties --------
+def test_full_size_720p_properties():
+    """At BASELINE.json's full size the oracle is too slow; use size-independent properties
+    (SURVEY section 8(c)): query == key => identity match, S ~ 1, interior T_lv3 == key, borders
+    attenuated by the constant /9; linearity of the transfer in the reference pyramid."""
+    torch.manual_seed(1)
+    h, w = 180, 320
+    k = torch.randn(1, 128, h, w, device="cuda") * 0.04
+    lv2 = torch.randn(1, 64, 2 * h, 2 * w, device="cuda") * 0.04
+    lv1 = torch.randn(1, 32, 4 * h, 4 * w, device="cuda") * 0.04
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(k.clone(), k, lv1, lv2, k, return_index=True)
+        ident = torch.arange(h * w, device="cuda")[None]
+        assert torch.equal(arg, ident)
+        assert float((S - 1).abs().max()) < 1e-5
+        torch.testing.assert_close(T3[:, :, 1:-1, 1:-1], k[:, :, 1:-1, 1:-1], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(T1[:, :, 4:-4, 4:-4], lv1[:, :, 4:-4, 4:-4], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(T3[:, :, 0, 0], k[:, :, 0, 0] * (4.0 / 9.0), rtol=1e-5, atol=1e-7)
+        # linearity: T(2*ref) == 2*T(ref) exactly (power-of-two scaling commutes with every rounding)
+        _, _, _, T1b = st(k.clone(), k, lv1 * 2, lv2, k)
+        assert torch.equal(T1b, T1 * 2)
+    assert st.last_stats.cpu().tolist()[0] == 0
+
+
+def test_full_size_720p_random_subset_vs_exhaustive_fp32():
+    """TC path vs the exhaustive fp32 CUDA-core search on the same staged operands, 720p, random data."""
+    torch.manual_seed(2)
+    h, w = 180, 320
+    q = torch.randn(1, 128, h, w, device="cuda") * 0.2
+    k = (torch.randn(1, 1, 128, h, w, device="cuda") * 0.04).contiguous()
+    S_tc, a_tc, stats, flag = U.run_search(q, k, search=_lib.SEARCH_TC)
+    S_ex, a_ex, _, _ = U.run_search(q, k, search=_lib.SEARCH_EXACT)
+    assert flag == 0
+    diff = (a_tc != a_ex)
+    # any disagreement must be a near tie in relevance
+    assert float((S_tc - S_ex).abs().max()) < 1e-5
+    assert int(diff.sum()) <= 0.001 * h * w
+
+
+# ------------------------------------------------------------------ boundary behaviour ----------
+def test_errors_are_loud():
+    st = speinet_b200.SearchTransfer().cuda()
+    q = torch.randn(1, 128, 8, 8, device="cuda")
+    with pytest.raises(RuntimeError, match="forward-only"):
+        st(q.clone().requires_grad_(True), q, torch.randn(1, 32, 32, 32, device="cuda"), torch.randn(1, 64, 16, 16, device="cuda"), q)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="expected"):
+        st(q, q, torch.randn(1, 32, 30, 32, device="cuda"), torch.randn(1, 64, 16, 16, device="cuda"), q)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="channels"):
+        st(torch.randn(1, 64, 8, 8, device="cuda"), torch.randn(1, 64, 8, 8, device="cuda"), None, None, None)
+    lib = speinet_b200.load_library()
+    shape = U.make_shape(1, 8, 8, 8, 8)
+    assert lib.spei_stage_norm(ctypes.byref(shape), U.vp(q), U.vp(q), ctypes.c_void_p(0), 0, U.cur_stream()) == -1
+    ws, ptr, nbytes = U.alloc_workspace(shape)
+    assert lib.spei_stage_norm(ctypes.byref(shape), U.vp(q), U.vp(q), ctypes.c_void_p(ptr), 16, U.cur_stream()) == -4
+
+
+def test_runs_on_non_default_stream_and_batch_mask():
+    """speinet.py:163 feeds boolean-mask sub-batches; inference may use side streams."""
+    torch.manual_seed(5)
+    q = torch.randn(3, 128, 12, 16, device="cuda") * 0.2
+    lv3 = torch.randn(3, 128, 12, 16, device="cuda") * 0.04
+    lv2 = torch.randn(3, 64, 24, 32, device="cuda") * 0.04
+    lv1 = torch.randn(3, 32, 48, 64, device="cuda") * 0.04
+    st = speinet_b200.SearchTransfer().cuda()
+    mask = torch.tensor([True, False, True], device="cuda")
+    with torch.no_grad():
+        full = st(q, lv3, lv1, lv2, lv3)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            sub = st(q[mask], lv3[mask], lv1[mask], lv2[mask], lv3[mask])
+        torch.cuda.current_stream().wait_stream(side)
+    for a, b in zip(full, sub):
+        assert torch.equal(a[mask], b)

@@ -1,0 +1,87 @@
+"""Host-side logic of the drop-in (no GPU): module surface, state-dict keys, error behaviour,
+clip sharding and the world-size-2 gather over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import oracle
+import speinet_b200
+from speinet_b200 import sharding
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    # SearchTransfer.py:10-11 (n_feat=32): search1 Conv2d(128->64,1x1), search2 Conv2d(64->32,1x1)
+    sd = speinet_b200.SearchTransfer().state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "search1.weight": (64, 128, 1, 1), "search1.bias": (64,),
+        "search2.weight": (32, 64, 1, 1), "search2.bias": (32,)}
+    sd2 = speinet_b200.SelfTransfer().state_dict()
+    assert sorted(sd2) == sorted(sd)
+
+
+def test_reference_checkpoint_loads_strict():
+    import importlib.util
+    ref_path = "/root/reference/model/SearchTransfer.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference not mounted")
+    spec = importlib.util.spec_from_file_location("_ref_st", ref_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ours = speinet_b200.SearchTransfer()
+    ours.load_state_dict(mod.SearchTransfer().state_dict(), strict=True)
+
+
+def test_bis_helper_matches_oracle():
+    st = speinet_b200.SearchTransfer()
+    x = torch.randn(2, 5, 7)
+    idx = torch.randint(0, 7, (2, 9))
+    got = st.bis(x, 2, idx).numpy()
+    assert np.array_equal(got, oracle.search_transfer_np.bis(x.numpy(), idx.numpy()))
+
+
+def test_cpu_tensors_raise_no_fallback():
+    st = speinet_b200.SearchTransfer()
+    q = torch.randn(1, 128, 8, 8)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA|cuda|libspeinet|missing"):
+        st(q, q, torch.randn(1, 32, 32, 32), torch.randn(1, 64, 16, 16), q)
+
+
+def test_shard_clips_round_robin():
+    assert sharding.shard_clips(64, 3, 8) == list(range(3, 64, 8))
+    all_ids = sorted(i for r in range(3) for i in sharding.shard_clips(10, r, 3))
+    assert all_ids == list(range(10))
+    with pytest.raises(ValueError):
+        sharding.shard_clips(4, 4, 4)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gather_worker(rank, world, port, num_clips, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ids = sharding.shard_clips(num_clips, rank, world)
+        local = torch.stack([torch.full((3, 4, 5), float(i)) for i in ids]) if ids else torch.empty(0, 3, 4, 5)
+        out = sharding.gather_outputs(local, num_clips, rank, world)
+        ret[rank] = out[:, 0, 0, 0].tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_clips", [4, 5])
+def test_gather_outputs_world2_gloo(num_clips):
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gather_worker, args=(world, port, num_clips, ret), nprocs=world, join=True)
+        for r in range(world):
+            assert ret[r] == [float(i) for i in range(num_clips)]
