@@ -3,18 +3,26 @@
 //
 //     out = dec + (W . cat(dec, T) + b) * bicubic_up(S, scale)
 //
-// fused into one pass: the concatenation is never materialised (two row ranges of one K loop), the
-// 1x1 convolution is a [C x 2C] x [2C x pixels] fp32 register-tiled GEMM, the x2 / x4 bicubic
-// upsampling of the one-channel map S (align_corners=False, A=-0.75, border-clamped taps,
-// torch/include/ATen/native/UpSample.h:289-300,400-423) is evaluated inline in the epilogue, and the
-// multiply + residual add are applied before the single store.
+// fused into one pass over HBM (read dec, read T, write out -- 3 x tensor size, the algorithmic
+// minimum): the concatenation is never materialised (two row ranges of one K loop), the x2 / x4
+// bicubic upsampling of the one-channel map S (align_corners=False, A=-0.75, border-clamped taps,
+// torch/include/ATen/native/UpSample.h:289-300,400-423) is evaluated inline, and bias, multiply and
+// residual add are applied before the single store.
+//
+// The 1x1 convolution is a skinny [C x 2C] x [2C x pixels] GEMM that must stay fp32-accurate (1e-4
+// bar) yet not become the bottleneck of an HBM-bound kernel, so it runs on the tensor cores with the
+// 3xTF32 split: x = hi + lo (both TF32), W.X ~= Wlo.Xhi + Whi.Xlo + Whi.Xhi with fp32 accumulation
+// (error ~2^-21 per product, i.e. fp32 class).  Operands are streamed through a double-buffered
+// cp.async pipeline; shared-memory pitches (W: K-chunk+4, X: 128+8 floats) make every mma.sync
+// fragment load bank-conflict free.
 #include "spei_common.cuh"
 
 namespace spei {
 
-constexpr int kFM = 32;   // output channels per block
-constexpr int kFN = 128;  // pixels per block
-constexpr int kFK = 32;   // input channels per step
+constexpr int kFN = 128;            // pixels per block
+constexpr int kFK = 32;             // input channels per pipeline step
+constexpr int kXP = kFN + 8;        // X pitch (floats): 8*k + n -> 32 distinct banks
+constexpr int kWP = kFK + 4;        // W pitch (floats): 4*m + k -> 32 distinct banks
 
 __device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 __device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
@@ -38,100 +46,180 @@ __device__ __forceinline__ float bicubic_tap(const float* __restrict__ S, int h,
   return rows[0] * cy[0] + rows[1] * cy[1] + rows[2] * cy[2] + rows[3] * cy[3];
 }
 
-// grid: (ceil(plane/128), C/32, n)   block: 256 = 32 pixel-quads x 8 channel-quads
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// grid: (ceil(plane/128), 1, n)   block: 256 = (C/32) warps along channels x the rest along pixels
+template <int C, bool kVec>
 __global__ void __launch_bounds__(256)
 fuse_level_kernel(const float* __restrict__ dec, const float* __restrict__ tt, const float* __restrict__ S,
-                  const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out, int C, int h,
-                  int w, int scale) {
-  __shared__ __align__(16) float Ws[kFK][kFM];
-  __shared__ __align__(16) float Xs[kFK][kFN];
+                  const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out, int h, int w,
+                  int scale) {
+  constexpr int K = 2 * C, WM = C / 32, WN = 8 / WM, WPX = kFN / WN, NTW = WPX / 8;
+  extern __shared__ __align__(16) float fsm[];
+  float (*Xs)[kFK][kXP] = reinterpret_cast<float (*)[kFK][kXP]>(fsm);                       // [2][32][136]
+  float (*Ws)[C][kWP] = reinterpret_cast<float (*)[C][kWP]>(fsm + 2 * kFK * kXP);           // [2][C][36]
+  float* sw = fsm + 2 * kFK * kXP + 2 * C * kWP;                                            // [128]
+
   const int hs = h * scale, wsz = w * scale;
   const size_t plane = (size_t)hs * wsz;
-  const int n = blockIdx.z, o0 = blockIdx.y * kFM;
+  const int n = blockIdx.z;
   const size_t p0 = (size_t)blockIdx.x * kFN;
-  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int wm = warp % WM, wn = warp / WM;
   const float* dec_n = dec + (size_t)n * C * plane;
   const float* t_n = tt + (size_t)n * C * plane;
 
-  float acc[4][4];
+  auto load_chunk = [&](int buf, int k0) {
+    if (kVec) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+      for (int it = 0; it < (kFK * kFN / 4) / 256; ++it) {
+        const int e = t + 256 * it, row = e >> 5, c4 = e & 31, ch = k0 + row;
+        const float* src = (ch < C ? dec_n + (size_t)ch * plane : t_n + (size_t)(ch - C) * plane) + p0 + c4 * 4;
+        cp_async16(&Xs[buf][row][c4 * 4], src, p0 + c4 * 4 < plane);
+      }
+    } else {
+#pragma unroll 4
+      for (int it = 0; it < (kFK * kFN) / 256; ++it) {
+        const int e = t + 256 * it, row = e >> 7, c = e & 127, ch = k0 + row;
+        const float* src = (ch < C ? dec_n + (size_t)ch * plane : t_n + (size_t)(ch - C) * plane) + p0 + c;
+        cp_async4(&Xs[buf][row][c], src, p0 + c < plane);
+      }
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int it = 0; it < (C * kFK / 4 + 255) / 256; ++it) {
+      const int e = t + 256 * it, row = e >> 3, c4 = e & 7;
+      if (row < C) cp_async16(&Ws[buf][row][c4 * 4], weight + (size_t)row * K + k0 + c4 * 4, true);
+    }
+    cp_async_commit();
+  };
 
-  const int K = 2 * C;
-  for (int k0 = 0; k0 < K; k0 += kFK) {
-    __syncthreads();
-    // weight chunk, transposed: Ws[k][o] = W[o0+o][k0+k]
-#pragma unroll
-    for (int it = 0; it < (kFK * kFM) / 256; ++it) {
-      // lanes walk the output channel so the shared-memory store is conflict-free; the strided global
-      // read hits a <=128 KB matrix that stays in L1/L2
-      const int e = t + 256 * it, oo = e & (kFM - 1), kk = e / kFM;
-      Ws[kk][oo] = __ldg(weight + (size_t)(o0 + oo) * K + k0 + kk);
-    }
-    // input chunk: rows k0..k0+31 of cat(dec, T)
-#pragma unroll
-    for (int it = 0; it < (kFK * kFN) / 256; ++it) {
-      const int e = t + 256 * it, pp = e & (kFN - 1), kk = e / kFN;
-      const int ch = k0 + kk;
-      const float* src = ch < C ? dec_n + (size_t)ch * plane : t_n + (size_t)(ch - C) * plane;
-      Xs[kk][pp] = (p0 + pp < plane) ? __ldg(src + p0 + pp) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kFK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&Ws[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-  }
-
-  // epilogue: soft-attention weight (bicubic upsampled S), bias, multiply, residual add
-  const float* S_n = S + (size_t)n * h * w;
-  const float rscale = 1.0f / (float)scale;
-  float sw[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const size_t p = p0 + tx * 4 + j;
-    sw[j] = 0.f;
+  load_chunk(0, 0);
+  // soft-attention weight of this block's pixels (bicubic upsampled S), once per block
+  if (t < kFN) {
+    const size_t p = p0 + t;
+    float v = 0.f;
     if (p < plane) {
       const int oy = (int)(p / wsz), ox = (int)(p % wsz);
-      sw[j] = scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : bicubic_tap(S_n, h, w, oy, ox, rscale);
+      const float* S_n = S + (size_t)n * h * w;
+      v = scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : bicubic_tap(S_n, h, w, oy, ox, 1.0f / (float)scale);
     }
+    sw[t] = v;
   }
-  const bool vec_ok = (plane & 3) == 0 && (p0 + tx * 4 + 3 < plane);
+
+  float acc[2][NTW][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int o = o0 + ty * 4 + i;
-    const float b = __ldg(bias + o);
-    const size_t idx0 = ((size_t)n * C + o) * plane + p0 + tx * 4;
-    if (vec_ok) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dec + idx0));
-      float4 r;
-      r.x = d.x + (acc[i][0] + b) * sw[0]; r.y = d.y + (acc[i][1] + b) * sw[1];
-      r.z = d.z + (acc[i][2] + b) * sw[2]; r.w = d.w + (acc[i][3] + b) * sw[3];
-      *reinterpret_cast<float4*>(out + idx0) = r;
-    } else {
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (p0 + tx * 4 + j < plane) out[idx0 + j] = __ldg(dec + idx0 + j) + (acc[i][j] + b) * sw[j];
+    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+  constexpr int NCH = K / kFK;
+  const int g = lane >> 2, q4 = lane & 3;
+  for (int kc = 0; kc < NCH; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < NCH) { load_chunk(buf ^ 1, (kc + 1) * kFK); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+#pragma unroll
+    for (int k8 = 0; k8 < kFK / 8; ++k8) {
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* wr = &Ws[buf][wm * 32 + mt * 16 + g][k8 * 8 + q4];
+        split_tf32(wr[0], ahi[mt][0], alo[mt][0]);
+        split_tf32(wr[8 * kWP], ahi[mt][1], alo[mt][1]);
+        split_tf32(wr[4], ahi[mt][2], alo[mt][2]);
+        split_tf32(wr[8 * kWP + 4], ahi[mt][3], alo[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const float* xr = &Xs[buf][k8 * 8 + q4][wn * WPX + nt * 8 + g];
+        uint32_t bhi[2], blo[2];
+        split_tf32(xr[0], bhi[0], blo[0]);
+        split_tf32(xr[4 * kXP], bhi[1], blo[1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_tf32(acc[mt][nt], alo[mt], bhi);   // small terms first
+          mma_tf32(acc[mt][nt], ahi[mt], blo);
+          mma_tf32(acc[mt][nt], ahi[mt], bhi);
+        }
+      }
     }
+    __syncthreads();
   }
+
+  // epilogue: bias, multiply by the soft-attention weight, residual add, one store
+  const bool pair_ok = (plane & 1) == 0;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int o = wm * 32 + mt * 16 + g + hh * 8;
+      const float b = __ldg(bias + o);
+      const size_t row = ((size_t)n * C + o) * plane;
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int pl = wn * WPX + nt * 8 + 2 * q4;
+        const size_t p = p0 + pl;
+        const float r0 = (acc[mt][nt][hh * 2 + 0] + b) * sw[pl], r1 = (acc[mt][nt][hh * 2 + 1] + b) * sw[pl + 1];
+        if (pair_ok && p + 1 < plane) {
+          const float2 d = __ldg(reinterpret_cast<const float2*>(dec + row + p));
+          *reinterpret_cast<float2*>(out + row + p) = make_float2(d.x + r0, d.y + r1);
+        } else {
+          if (p < plane) out[row + p] = __ldg(dec + row + p) + r0;
+          if (p + 1 < plane) out[row + p + 1] = __ldg(dec + row + p + 1) + r1;
+        }
+      }
+    }
+}
+
+template <int C, bool kVec>
+static int launch_fuse_t(int n, int h, int w, int scale, const float* dec, const float* t, const float* S, const float* weight,
+                         const float* bias, float* out, cudaStream_t st) {
+  const size_t plane = (size_t)h * scale * w * scale;
+  const int smem = (2 * kFK * kXP + 2 * C * kWP + kFN) * (int)sizeof(float);
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_kernel<C, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((unsigned)((plane + kFN - 1) / kFN), 1, n);
+  fuse_level_kernel<C, kVec><<<grid, 256, smem, st>>>(dec, t, S, weight, bias, out, h, w, scale);
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
 }
 
 int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
                       const float* weight, const float* bias, float* out, cudaStream_t st) {
-  const size_t plane = (size_t)h * scale * w * scale;
   if (n > 65535) { set_error("fuse_level: n too large"); return SPEI_ERR_ARG; }
-  dim3 grid((unsigned)((plane + kFN - 1) / kFN), c / kFM, n);
-  fuse_level_kernel<<<grid, 256, 0, st>>>(dec, t, S, weight, bias, out, c, h, w, scale);
-  SPEI_CUDA(cudaGetLastError());
-  return SPEI_OK;
+  const size_t plane = (size_t)h * scale * w * scale;
+  const bool vec = (plane % 4) == 0;
+#define FUSE(C_) (vec ? launch_fuse_t<C_, true>(n, h, w, scale, dec, t, S, weight, bias, out, st) \
+                      : launch_fuse_t<C_, false>(n, h, w, scale, dec, t, S, weight, bias, out, st))
+  if (c == 128) return FUSE(128);
+  if (c == 64) return FUSE(64);
+  if (c == 32) return FUSE(32);
+#undef FUSE
+  set_error("fuse_level: unsupported channel count %d", c);
+  return SPEI_ERR_ARG;
 }
 
 }  // namespace spei

@@ -41,7 +41,9 @@ constexpr uint32_t kQLBO = (kQTileV + 2) * kRowBytes;                       // 2
 constexpr uint32_t kStageBytesMax = kCGS * (kMaxNy + 2) * kRowBytes;        // 21760
 constexpr uint32_t kStagesPerTile = kCG / kCGS;                             // 4
 constexpr uint32_t kNumBars = 2 * kStages + 6;
-constexpr uint32_t kSmemBytes = kQTileBytes + kStages * kStageBytesMax + kNumBars * 8 + 16;
+constexpr uint32_t kRkSmemOffset = kQTileBytes + kStages * kStageBytesMax + kNumBars * 8 + 16;  // 4 warps x 256 floats
+constexpr uint32_t kSmemBytes = kRkSmemOffset + 4 * 256 * 4;
+static_assert(kRkSmemOffset % 16 == 0, "key-norm staging must be float4 aligned");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCols = 256;
 
@@ -139,6 +141,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 struct PairIdx { int item, qt, kt; };
+__device__ __forceinline__ PairIdx next_pair(PairIdx r, int QT, int KT) {
+  if (++r.kt == KT) { r.kt = 0; if (++r.qt == QT) { r.qt = 0; ++r.item; } }
+  return r;
+}
 __device__ __forceinline__ PairIdx decode_pair(long long p, int QT, int KT) {
   PairIdx r;
   const long long per_item = (long long)QT * KT;
@@ -186,8 +192,8 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       int qloaded = 0;
-      for (long long pp = pb; pp < pe; ++pp) {
-        const PairIdx ix = decode_pair(pp, p.QT, p.KT);
+      PairIdx ix = decode_pair(pb, p.QT, p.KT);
+      for (long long pp = pb; pp < pe; ++pp, ix = next_pair(ix, p.QT, p.KT)) {
         if (pp == pb || ix.kt == 0) {
           if (qloaded > 0) mbar_wait(bar_qfree, (uint32_t)((qloaded - 1) & 1), p.error_flag);
           const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
@@ -215,8 +221,8 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       // byte offset of patch tap (ki,kj) inside a halo tile, per operand orientation
       const uint32_t q_dki = p.q_orient == 0 ? kRowBytes : 16u, q_dkj = p.q_orient == 0 ? 16u : kRowBytes;
       const uint32_t k_dki = p.k_orient == 0 ? kRowBytes : 16u, k_dkj = p.k_orient == 0 ? 16u : kRowBytes;
-      for (long long pp = pb; pp < pe; ++pp, ++tile_i) {
-        const PairIdx ix = decode_pair(pp, p.QT, p.KT);
+      PairIdx ix = decode_pair(pb, p.QT, p.KT);
+      for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
         if (pp == pb || ix.kt == 0) {
           mbar_wait(bar_qfull, (uint32_t)(qused & 1), p.error_flag);
           ++qused;
@@ -256,8 +262,24 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int ti[kTopK];
     uint32_t tile_i = 0;
     long long qlin = -1;
-    for (long long pp = pb; pp < pe; ++pp, ++tile_i) {
-      const PairIdx ix = decode_pair(pp, p.QT, p.KT);
+    float* rk_s = reinterpret_cast<float*>(smem + kRkSmemOffset) + ew * kAccCols;  // this warp's copy of the tile's key norms
+    const int nchunk = p.Ny / 2;
+    // key-norm prefetch: lane l owns float4 #l and #(l+32) of the tile's [Ny][8] reciprocal norms
+    auto rk_prefetch = [&](const PairIdx ix, float4 (&pre)[2]) {
+      const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
+      const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
+      const float* rkrow = p.rkpad + ((size_t)(ix.item * p.rf + f) * p.VkT + ktv * p.Ny) * p.UkT + ktu * kTileU;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e4 = lane + 32 * j, row = e4 >> 1;
+        pre[j] = row < p.Ny ? __ldg(reinterpret_cast<const float4*>(rkrow + (size_t)row * p.UkT) + (e4 & 1))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 pre[2];
+    PairIdx ix = decode_pair(pb, p.QT, p.KT);
+    if (pb < pe) rk_prefetch(ix, pre);
+    for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
       if (pp == pb || ix.kt == 0) {
 #pragma unroll
         for (int s = 0; s < kTopK; ++s) { tv[s] = -INFINITY; ti[s] = -1; }
@@ -269,38 +291,61 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
       const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
       const int ku0 = ktu * kTileU, kv0 = ktv * p.Ny;
-      const float* rkrow = p.rkpad + ((size_t)(ix.item * p.rf + f) * p.VkT + kv0) * p.UkT + ku0;
+      // publish this tile's key norms to the warp (the loads were issued one tile ago), then start the
+      // loads for the next tile so their latency hides behind this tile's work
+      __syncwarp();
+      reinterpret_cast<float4*>(rk_s)[lane] = pre[0];
+      reinterpret_cast<float4*>(rk_s)[lane + 32] = pre[1];
+      __syncwarp();
+      if (pp + 1 < pe) rk_prefetch(next_pair(ix, p.QT, p.KT), pre);
       mbar_wait(bar_tfull + 8 * acc, use & 1u, p.error_flag);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(ew * 32) << 16);
-      for (int r2 = 0; r2 < p.Ny / 2; ++r2) {
-        uint32_t a[16];
-        tc_ld16(taddr + r2 * 16, a);
-        float rk[16];
-        {
-          const float4* r0 = reinterpret_cast<const float4*>(rkrow + (size_t)(2 * r2) * p.UkT);
-          const float4* r1 = reinterpret_cast<const float4*>(rkrow + (size_t)(2 * r2 + 1) * p.UkT);
-          const float4 x0 = __ldg(r0), x1 = __ldg(r0 + 1), x2 = __ldg(r1), x3 = __ldg(r1 + 1);
-          rk[0] = x0.x; rk[1] = x0.y; rk[2] = x0.z; rk[3] = x0.w; rk[4] = x1.x; rk[5] = x1.y; rk[6] = x1.z; rk[7] = x1.w;
-          rk[8] = x2.x; rk[9] = x2.y; rk[10] = x2.z; rk[11] = x2.w; rk[12] = x3.x; rk[13] = x3.y; rk[14] = x3.z; rk[15] = x3.w;
-        }
+
+      // TMEM reads are double-buffered in registers: chunk c+1 is in flight while chunk c is processed.
+      // The code below exists once (copying 16 registers is cheaper than a second inlined copy: the
+      // epilogue shares the SM's instruction cache with the MMA issuer, and a fat epilogue starves it).
+      uint32_t a[16];
+      tc_ld16(taddr, a);
+      for (int r2 = 0; r2 < nchunk; ++r2) {
         tc_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 r = reinterpret_cast<const float4*>(rk_s + r2 * 16)[i4];  // broadcast read
+          v[4 * i4 + 0] = __uint_as_float(a[4 * i4 + 0]) * r.x;  // NaN for padded keys
+          v[4 * i4 + 1] = __uint_as_float(a[4 * i4 + 1]) * r.y;
+          v[4 * i4 + 2] = __uint_as_float(a[4 * i4 + 2]) * r.z;
+          v[4 * i4 + 3] = __uint_as_float(a[4 * i4 + 3]) * r.w;
+        }
         if (p.debug_acc && pp == 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) p.debug_acc[(size_t)m * kAccCols + r2 * 16 + i] = __uint_as_float(a[i]);
         }
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) * rk[i];  // NaN for padded keys
+        if (r2 + 1 < nchunk) tc_ld16(taddr + (r2 + 1) * 16, a);  // v[] holds this chunk; refill a[] asynchronously
         float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
         mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]))));
         if (mx > tv[kTopK - 1]) {
-          // rare after the first few tiles: sorted insertion, strict '>' keeps earlier keys ahead on ties
+          // compact slow path (taken by ~1 chunk in 4 per warp at 720p): bit mask of the qualifying
+          // columns, then one sorted insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
+          const float thr = tv[kTopK - 1];
+          unsigned msk = 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (v[i] > tv[kTopK - 1]) {
+          for (int i = 0; i < 16; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
+          while (msk) {
+            const int i = __ffs(msk) - 1;
+            msk &= msk - 1;
+            // 16-way register select as a 4-level tree on the bits of i
+            float s8[8], s4[4], s2[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s8[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = (i & 2) ? s8[2 * j + 1] : s8[2 * j];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) s2[j] = (i & 4) ? s4[2 * j + 1] : s4[2 * j];
+            float x = (i & 8) ? s2[1] : s2[0];
+            if (x > tv[kTopK - 1]) {
               const int ku = ku0 + (i & 7), kv = kv0 + 2 * r2 + (i >> 3);
-              float x = v[i];
               int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku, kv, p.Wr);
 #pragma unroll
               for (int s = 0; s < kTopK; ++s) {

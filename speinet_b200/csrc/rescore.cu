@@ -189,10 +189,10 @@ exact_search_kernel(const ExactParams p) {
   const int n = blockIdx.z;
   const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
   const int nq = p.list ? __ldg(p.list_count + n) : L;
-  const int qb = blockIdx.x * kEQ;
-  if (qb >= nq) return;
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int lq = t & 63, lpart = t >> 6;  // loader role: one of 64 rows, 8 of the 32 channels
+  // grid-stride over blocks of 64 queries: the queued-query count is only known on the device
+  for (int qb = blockIdx.x * kEQ; qb < nq; qb += gridDim.x * kEQ) {
 
   // loader: this thread's query
   int my_q = -1, my_qy = 0, my_qx = 0;
@@ -283,6 +283,7 @@ exact_search_kernel(const ExactParams p) {
     }
     if (tx == 0 && cq[i] >= 0) atomicMax(p.packed + (size_t)n * L + cq[i], b);
   }
+  }  // query blocks
 }
 
 __global__ void __launch_bounds__(256)
@@ -369,8 +370,9 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   e.list = r.flag_list; e.list_count = r.flag_count;
   const int L = p.H * p.W, qblocks = (L + kEQ - 1) / kEQ;
   const int max_splits = (p.rf * p.Hr * p.Wr + kEK - 1) / kEK;
-  e.key_splits = max_splits < 32 ? max_splits : 32;
-  exact_search_kernel<<<dim3(qblocks, e.key_splits, p.n), 256, 0, st>>>(e);
+  // few queries are expected here: many key splits (short serial loops), few query-block columns
+  e.key_splits = max_splits < 450 ? max_splits : 450;
+  exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());
   unpack_kernel<<<dim3(148, 1, p.n), 256, 0, st>>>(e.packed, e.list, e.list_count, L, S, arg32, arg64);
   SPEI_CUDA(cudaGetLastError());
