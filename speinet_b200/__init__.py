@@ -8,6 +8,7 @@ from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .search_transfer import SearchTransfer, SelfTransfer, search_transfer  # noqa: F401
 from .fusion import fuse_level, decode_fused, install  # noqa: F401
 from .sharding import shard_clips, gather_outputs  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
 __all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "decode_fused", "install",
-           "shard_clips", "gather_outputs", "load_library", "LIB_PATH"]
+           "shard_clips", "gather_outputs", "HostPipeline", "load_library", "LIB_PATH"]

@@ -350,3 +350,98 @@ def test_runs_on_non_default_stream_and_batch_mask():
         torch.cuda.current_stream().wait_stream(side)
     for a, b in zip(full, sub):
         assert torch.equal(a[mask], b)
+
+
+# ------------------------------------------------------------------ host pipeline / install ------
+def test_host_pipeline_matches_direct_calls():
+    torch.manual_seed(13)
+    h, w = 12, 16
+    mk = lambda *s, std: (torch.randn(*s) * std).pin_memory()
+    clips = [{"q": mk(1, 128, h, w, std=0.2), "lv3": mk(1, 128, h, w, std=0.04), "lv2": mk(1, 64, 2 * h, 2 * w, std=0.04),
+              "lv1": mk(1, 32, 4 * h, 4 * w, std=0.04), "dec3": mk(1, 128, h, w, std=0.3),
+              "dec2": mk(1, 64, 2 * h, 2 * w, std=0.3), "dec1": mk(1, 32, 4 * h, 4 * w, std=0.3)} for _ in range(5)]
+    convs = {3: torch.nn.Conv2d(256, 128, 1).cuda(), 2: torch.nn.Conv2d(128, 64, 1).cuda(), 1: torch.nn.Conv2d(64, 32, 1).cuda()}
+    wb = {l: (c.weight.detach(), c.bias.detach()) for l, c in convs.items()}
+    outs = [{"S": torch.empty(1, 1, h, w).pin_memory(), "f3": torch.empty(1, 128, h, w).pin_memory(),
+             "f2": torch.empty(1, 64, 2 * h, 2 * w).pin_memory(), "f1": torch.empty(1, 32, 4 * h, 4 * w).pin_memory()} for _ in range(5)]
+    pipe = speinet_b200.HostPipeline(wb, "cuda")
+    pipe.run(clips, outs)
+    torch.cuda.synchronize()
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        for clip, out in zip(clips, outs):
+            d = {k: v.cuda() for k, v in clip.items()}
+            S, T3, T2, T1 = st(d["q"], d["lv3"], d["lv1"], d["lv2"], d["lv3"])
+            f1 = speinet_b200.fuse_level(d["dec1"], T1, S, *wb[1], 4)
+            f3 = speinet_b200.fuse_level(d["dec3"], T3, S, *wb[3], 1)
+            assert torch.equal(out["S"], S.cpu()) and torch.equal(out["f1"], f1.cpu()) and torch.equal(out["f3"], f3.cpu())
+
+
+class _TinyRecons(torch.nn.Module):
+    """Stand-in with the attribute names decode_fused touches (recons_video_ori.py decoders / outBlock)."""
+    def __init__(self):
+        super().__init__()
+        self.decoder_second = torch.nn.ConvTranspose2d(128, 64, 3, stride=2, padding=1, output_padding=1)
+        self.decoder_first = torch.nn.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1)
+        self.outBlock = torch.nn.Conv2d(32, 3, 3, padding=1)
+
+
+class _TinySPEINet(torch.nn.Module):
+    """The parameters of SPEINet that _decode uses (speinet.py:53-66), reference-style PyTorch _decode."""
+    def __init__(self):
+        super().__init__()
+        import torch.nn as nn
+        n_feat = 32
+        self.recons_net = _TinyRecons()
+        self.SearchTransfer = speinet_b200.SearchTransfer()
+        self.SelfTransfer = speinet_b200.SelfTransfer()
+        self.conv_lv1 = nn.Conv2d(n_feat * 2, n_feat, 1)
+        self.conv_lv2 = nn.Conv2d(n_feat * 4, n_feat * 2, 1)
+        self.conv_lv3 = nn.Conv2d(n_feat * 8, n_feat * 4, 1)
+        self.search3 = nn.Conv2d(n_feat * 2, n_feat * 2, 3, padding=1)
+        self.search2 = nn.Conv2d(n_feat * 4, n_feat * 2, 1)
+        self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, 1)
+        self.search43 = nn.Conv2d(n_feat, n_feat, 3, padding=1)
+        self.search33 = nn.Conv2d(n_feat * 2, n_feat, 3, padding=1)
+        self.search13 = nn.Conv2d(n_feat * 2, n_feat, 1)
+
+    def _decode(self, f, S, T3, T2, T1):  # torch restatement of speinet.py:92-120 (the checker for decode_fused)
+        import torch.nn.functional as F
+        up = lambda x, s=2: F.interpolate(x, scale_factor=s, mode="bicubic")
+        f_lv3 = fuse_level_torch(f, T3, S, self.conv_lv3.weight, self.conv_lv3.bias, 1)
+        d2 = self.recons_net.decoder_second(f_lv3)
+        f_lv2 = fuse_level_torch(d2, T2, S, self.conv_lv2.weight, self.conv_lv2.bias, 2)
+        s1 = F.relu(self.search1(up(f_lv3)))
+        s2 = F.relu(self.search3(f_lv2))
+        f_v3 = d2 + F.relu(self.search2(torch.cat((d2, s1), 1)))
+        f_lv2 = f_lv2 + F.relu(self.search2(torch.cat((f_lv2, s2), 1)))
+        d1 = self.recons_net.decoder_first(f_lv2)
+        f_lv1 = fuse_level_torch(d1, T1, S, self.conv_lv1.weight, self.conv_lv1.bias, 4)
+        s13 = F.relu(self.search13(up(f_v3)))
+        s23 = F.relu(self.search33(up(f_lv2)))
+        s33 = F.relu(self.search43(f_lv1))
+        pair = lambda a, b: F.relu(self.search33(torch.cat((a, b), 1)))
+        return self.recons_net.outBlock(f_lv1 + pair(s13, s23) + pair(s13, s33) + pair(s23, s33))
+
+
+def test_install_and_decode_fused_match_torch_decode():
+    torch.manual_seed(17)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net = _TinySPEINet().cuda().eval()
+        h, w = 10, 14
+        f = torch.randn(2, 128, h, w, device="cuda") * 0.2
+        lv3 = torch.randn(2, 128, h, w, device="cuda") * 0.04
+        lv2 = torch.randn(2, 64, 2 * h, 2 * w, device="cuda") * 0.04
+        lv1 = torch.randn(2, 32, 4 * h, 4 * w, device="cuda") * 0.04
+        with torch.no_grad():
+            S, T3, T2, T1 = net.SearchTransfer(f, lv3, lv1, lv2, lv3)
+            want = net._decode(f, S, T3, T2, T1)
+            sd_before = {k: v.clone() for k, v in net.state_dict().items()}
+            speinet_b200.install(net)
+            assert sorted(net.state_dict()) == sorted(sd_before)          # checkpoint keys survive install()
+            got = net._decode(f, S, T3, T2, T1)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
