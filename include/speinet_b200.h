@@ -57,7 +57,8 @@ typedef struct SpeiShape {
 
 /* Counters written by spei_search_transfer into caller memory (device, 4 x int32) when
  * `stats` is non-NULL: [0] queries re-searched exhaustively in fp32 (candidate list saturated),
- * [1] candidates rescored in fp32, [2..3] reserved. */
+ * [1] candidates rescored in fp32, [2] max |bf16 candidate score - exact score| x 1e9 over rescored
+ * candidates (evidence for the eps window), [3] reserved. */
 
 int spei_version(void);
 const char *spei_last_error(void);

@@ -7,7 +7,7 @@ host-side mirror of the reference interface (`SearchTransfer`, `SelfTransfer`, `
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .search_transfer import SearchTransfer, SelfTransfer, search_transfer  # noqa: F401
 from .fusion import fuse_level, decode_fused, install  # noqa: F401
-from .sharding import shard_clips, gather_outputs  # noqa: F401
+from .sharding import shard_clips, gather_outputs, row_band, search_transfer_rows, gather_rows  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 
 __all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "decode_fused", "install",

@@ -123,18 +123,22 @@ rescore_kernel(const RescoreParams p) {
   // pass 2: exact relevance of every kept candidate
   unsigned long long best = 0ull;
   int nres = 0;
+  float max_err = 0.f;  // largest |bf16 score - exact score| seen: evidence for the eps window
   for (int e0 = 0; e0 < ncand; e0 += 32) {
     const int e = e0 + lane;
     int j = -1;
+    float vb = 0.f;
     if (e < ncand) {
       j = __ldg(ci + e);
-      if (j >= 0 && !(__ldg(cv + e) * rq >= thr)) j = -1;
+      vb = __ldg(cv + e) * rq;
+      if (j >= 0 && !(vb >= thr)) j = -1;
     }
     unsigned m = __ballot_sync(0xffffffffu, j >= 0);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int jj = __shfl_sync(0xffffffffu, j, src);
+      const float vbb = __shfl_sync(0xffffffffu, vb, src);
       const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
       const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
       double acc = 0.0;
@@ -155,6 +159,7 @@ rescore_kernel(const RescoreParams p) {
       const float score = (float)(acc * (double)rq * (double)rk);
       const unsigned long long key = pack_score(score, jj);
       best = key > best ? key : best;
+      max_err = fmaxf(max_err, fabsf(vbb - score));
       ++nres;
     }
   }
@@ -163,7 +168,10 @@ rescore_kernel(const RescoreParams p) {
     const int j = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
     p.S[wq] = s; p.arg32[wq] = j;
     if (p.arg64) p.arg64[wq] = j;
-    if (p.stats) atomicAdd(p.stats + 1, nres);
+    if (p.stats) {
+      atomicAdd(p.stats + 1, nres);
+      atomicMax(p.stats + 2, (int)(max_err * 1e9f));
+    }
   }
 }
 
@@ -173,6 +181,7 @@ rescore_kernel(const RescoreParams p) {
 struct ExactParams {
   int n, rf, H, W, Hr, Wr;
   int key_splits;
+  int small_max;              // list mode: items with <= small_max queued queries belong to exact_small_kernel
   const float *q32, *k32, *rq, *rk;
   const int32_t* list;        // [n][L] query ids, or NULL = all queries
   const int32_t* list_count;  // [n], or NULL
@@ -189,6 +198,7 @@ exact_search_kernel(const ExactParams p) {
   const int n = blockIdx.z;
   const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
   const int nq = p.list ? __ldg(p.list_count + n) : L;
+  if (p.list && nq <= p.small_max) return;  // handled by exact_small_kernel
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int lq = t & 63, lpart = t >> 6;  // loader role: one of 64 rows, 8 of the 32 channels
   // grid-stride over blocks of 64 queries: the queued-query count is only known on the device
@@ -286,6 +296,61 @@ exact_search_kernel(const ExactParams p) {
   }  // query blocks
 }
 
+// Few queued queries (the common case: a handful per frame): the 64-query tile of the kernel above
+// would be almost empty, so a warp brute-forces (query, key) pairs instead -- the query's 9x128 patch
+// lives in registers, each key costs nine coalesced 512-byte reads and an fp64 dot, exactly the
+// arithmetic of rescore_kernel.  grid: (key blocks, 1, n); items with more than kSmallMax queued
+// queries are left to exact_search_kernel (which skips the others).
+constexpr int kSmallMax = 64;
+
+__global__ void __launch_bounds__(256)
+exact_small_kernel(const ExactParams p) {
+  const int n = blockIdx.z;
+  const int cnt = __ldg(p.list_count + n);
+  if (cnt == 0 || cnt > kSmallMax) return;
+  const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (Lk + gridDim.x - 1) / gridDim.x;
+  const int k_lo = blockIdx.x * per, k_hi = min(Lk, k_lo + per);
+  const float* qimg = p.q32 + (size_t)n * L * kC3;
+  for (int qi = 0; qi < cnt; ++qi) {
+    const int q = __ldg(p.list + (size_t)n * L + qi);
+    const int y = q / p.W, x = q % p.W;
+    const float rq = __ldg(p.rq + (size_t)n * L + q);
+    float4 qv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      qv[t] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+                  ? __ldg(reinterpret_cast<const float4*>(qimg + ((size_t)yy * p.W + xx) * kC3) + lane)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    unsigned long long best = 0ull;
+    for (int j = k_lo + warp; j < k_hi; j += 8) {
+      const int f = j / lk1, rem = j - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
+      const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
+        if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
+          const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
+          acc = fma((double)qv[t].x, (double)kv.x, acc);
+          acc = fma((double)qv[t].y, (double)kv.y, acc);
+          acc = fma((double)qv[t].z, (double)kv.z, acc);
+          acc = fma((double)qv[t].w, (double)kv.w, acc);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
+      const unsigned long long key = pack_score((float)(acc * (double)rq * (double)rk), j);
+      best = key > best ? key : best;
+    }
+    if (lane == 0 && best) atomicMax(p.packed + (size_t)n * L + q, best);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 clear_packed_kernel(unsigned long long* packed, int32_t* flag_count, size_t total, int n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +437,10 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   const int max_splits = (p.rf * p.Hr * p.Wr + kEK - 1) / kEK;
   // few queries are expected here: many key splits (short serial loops), few query-block columns
   e.key_splits = max_splits < 450 ? max_splits : 450;
+  e.small_max = kSmallMax;
+  const int key_blocks = (p.rf * p.Hr * p.Wr + 63) / 64;
+  exact_small_kernel<<<dim3(key_blocks < 592 ? key_blocks : 592, 1, p.n), 256, 0, st>>>(e);
+  SPEI_CUDA(cudaGetLastError());
   exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());
   unpack_kernel<<<dim3(148, 1, p.n), 256, 0, st>>>(e.packed, e.list, e.list_count, L, S, arg32, arg64);

@@ -44,3 +44,52 @@ def gather_outputs(local: torch.Tensor, num_clips: int, rank: int, world: int, g
         if ids:
             out[ids] = recv[r, :len(ids)]
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Single very large frame: shard the QUERY ROWS of the lv3 grid (second row)
+# --------------------------------------------------------------------------------------------------
+def row_band(h: int, rank: int, world: int):
+    """Rows [y0, y1) of the lv3 query grid owned by `rank`, and the padded band [p0, p1) it must search.
+
+    T at row y needs the argmax of rows y-1..y+1 (3x3 fold neighbourhood) and the patch of row y needs
+    pixel rows y-1..y+1, so the searched band carries a 2-row halo; recomputing the halo instead of
+    exchanging indices keeps the path free of any data-path collective.  Unlike the reference's
+    `forward_chop` quadrants (inference_SPEINet.py:545-607) every band still searches ALL keys, so
+    the result is identical to the unsharded one."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    y0, y1 = rank * h // world, (rank + 1) * h // world
+    return y0, y1, max(0, y0 - 2), min(h, y1 + 2)
+
+
+def search_transfer_rows(module, lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, rank: int, world: int):
+    """This rank's row band of SearchTransfer.forward for one large frame: returns
+    (S, T_lv3, T_lv2, T_lv1) restricted to lv3 rows [y0, y1) (x1 / x2 / x4 for the pyramid levels)."""
+    h = lrsr_lv3.shape[2]
+    y0, y1, p0, p1 = row_band(h, rank, world)
+    if y1 <= y0:
+        raise ValueError(f"rank {rank} of {world} owns no rows of a {h}-row grid")
+    S, T3, T2, T1 = module(lrsr_lv3[:, :, p0:p1].contiguous(), refsr_lv3, ref_lv1, ref_lv2, ref_lv3)
+    a, b = y0 - p0, y1 - p0
+    return (S[:, :, a:b], T3[:, :, a:b], T2[:, :, 2 * a:2 * b], T1[:, :, 4 * a:4 * b])
+
+
+def gather_rows(parts, h: int, rank: int, world: int, group=None):
+    """All-gather the row bands of `search_transfer_rows` into full-height tensors (NCCL or gloo).
+    `parts` = (S, T_lv3, T_lv2, T_lv1) bands of this rank; returns the four full tensors."""
+    if world == 1:
+        return tuple(parts)
+    out = []
+    for t, s in zip(parts, (1, 1, 2, 4)):
+        full = t.new_empty(t.shape[:2] + (h * s,) + t.shape[3:])
+        per = max(((r + 1) * h // world - r * h // world) for r in range(world)) * s
+        send = t.new_zeros(t.shape[:2] + (per,) + t.shape[3:])
+        send[:, :, :t.shape[2]] = t
+        recv = t.new_empty((world,) + tuple(send.shape))
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+        for r in range(world):
+            y0, y1 = r * h // world, (r + 1) * h // world
+            full[:, :, y0 * s:y1 * s] = recv[r][:, :, :(y1 - y0) * s]
+        out.append(full)
+    return tuple(out)

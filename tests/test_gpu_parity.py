@@ -445,3 +445,22 @@ def test_install_and_decode_fused_match_torch_decode():
         torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_frame_equals_unsharded(world):
+    """Single large frame split by query rows: the bands of all ranks, computed
+    one after the other on this GPU, stitch to exactly the unsharded result."""
+    torch.manual_seed(23)
+    h, w = 26, 24
+    q = torch.randn(1, 128, h, w, device="cuda") * 0.2
+    lv3 = torch.randn(1, 128, 20, 28, device="cuda") * 0.04
+    lv2 = torch.randn(1, 64, 40, 56, device="cuda") * 0.04
+    lv1 = torch.randn(1, 32, 80, 112, device="cuda") * 0.04
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        full = st(q, lv3, lv1, lv2, lv3)
+        bands = [speinet_b200.search_transfer_rows(st, q, lv3, lv1, lv2, lv3, r, world) for r in range(world)]
+    for i in range(4):
+        stitched = torch.cat([b[i] for b in bands], dim=2)
+        assert torch.equal(stitched, full[i]), f"output {i} differs between row-sharded and unsharded"

@@ -85,3 +85,38 @@ def test_gather_outputs_world2_gloo(num_clips):
         mp.spawn(_gather_worker, args=(world, port, num_clips, ret), nprocs=world, join=True)
         for r in range(world):
             assert ret[r] == [float(i) for i in range(num_clips)]
+
+
+@pytest.mark.parametrize("h,world", [(180, 8), (120, 3), (7, 2), (5, 1)])
+def test_row_bands_tile_the_grid_with_two_row_halo(h, world):
+    covered = []
+    for r in range(world):
+        y0, y1, p0, p1 = sharding.row_band(h, r, world)
+        covered += list(range(y0, y1))
+        assert p0 == max(0, y0 - 2) and p1 == min(h, y1 + 2)
+    assert covered == list(range(h))
+
+
+def _rows_worker(rank, world, port, h, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        y0, y1, _, _ = sharding.row_band(h, rank, world)
+        rows = torch.arange(h, dtype=torch.float32)
+        band = lambda s: rows.repeat_interleave(s)[y0 * s:y1 * s].view(1, 1, -1, 1).expand(1, 2, -1, 3).contiguous()
+        full = sharding.gather_rows((band(1), band(1), band(2), band(4)), h, rank, world)
+        ret[rank] = [t[0, 0, :, 0].tolist() for t in full]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    world, port, h = 2, _free_port(), 7   # ragged: bands of 3 and 4 rows
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_rows_worker, args=(world, port, h, ret), nprocs=world, join=True)
+        rows = torch.arange(h, dtype=torch.float32)
+        for r in range(world):
+            for got, s in zip(ret[r], (1, 1, 2, 4)):
+                assert got == rows.repeat_interleave(s).tolist()

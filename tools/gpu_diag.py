@@ -174,6 +174,70 @@ def timed(fn, iters=5, warm=2):
     return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))[iters // 2]
 
 
+def stage_robust():
+    """Image-like (smooth, self-similar) features at full 720p size: how many queries saturate their
+    candidate list, what the fallback costs, and whether the result still equals the exhaustive fp32 search."""
+    import torch.nn.functional as F
+    torch.manual_seed(4)
+    h, w = 180, 320
+    out = []
+    for name, smooth, noise, shift in (("smooth_x8", 8, 0.02, (2, 3)), ("smooth_x4", 4, 0.05, (1, 1)), ("smooth_x16_lownoise", 16, 0.005, (3, 5)),
+                                       ("randn", 0, 0.0, (0, 0))):
+        if smooth:
+            base = torch.randn(1, 128, h // smooth + 4, w // smooth + 4, device="cuda")
+            up = F.interpolate(base, scale_factor=smooth, mode="bicubic")
+            q = (up[:, :, :h, :w] + noise * torch.randn(1, 128, h, w, device="cuda")).contiguous() * 0.2
+            k = (up[:, :, shift[0]:shift[0] + h, shift[1]:shift[1] + w] + noise * torch.randn(1, 128, h, w, device="cuda")).contiguous() * 0.2
+        else:
+            q = torch.randn(1, 128, h, w, device="cuda") * 0.2
+            k = torch.randn(1, 128, h, w, device="cuda") * 0.04
+        k5 = k.unsqueeze(1).contiguous()
+        t0 = time.time()
+        S, a, st, fl = U.run_search(q, k5)
+        t_tc = time.time() - t0
+        ms = timed(lambda: U.run_search(q, k5), iters=3, warm=1)
+        S2, a2, _, _ = U.run_search(q, k5, search=_lib.SEARCH_EXACT)
+        diff = (a != a2)
+        r = {"case": name, "stats": st.cpu().tolist(), "error_flag": fl, "ms_search_incl_host_overhead": ms,
+             "index_mismatch_vs_exhaustive": int(diff.sum()), "S_max_abs_diff": float((S - S2).abs().max()),
+             "S_mean": float(S.mean()), "first_call_s": t_tc}
+        for eps in (1e-3, 4e-3, 8e-3):  # 8e-3 = rigorous two-sided worst-case bound 2^-7 of bf16 operand rounding
+            Se, ae, ste, _ = U.run_search(q, k5, eps=eps)
+            mse = timed(lambda: U.run_search(q, k5, eps=eps), iters=3, warm=1)
+            r[f"eps_{eps:g}"] = {"stats": ste.cpu().tolist(), "ms": mse, "mismatch_vs_exhaustive": int((ae != a2).sum())}
+        out.append(r)
+        print("robust", r, flush=True)
+    REC["robust"] = out
+
+
+def stage_configs():
+    """The other BASELINE.json configs through the public module: 256x256 (64x64 grid), BSD 640x480 with two
+    sharp frames and batch 8 (configs[3]), 720p SelfTransfer; module-level time incl. host overhead."""
+    import speinet_b200
+    torch.manual_seed(6)
+    st = speinet_b200.SearchTransfer().cuda()
+    out = {}
+    for name, n, h, w, rf in (("256x256", 1, 64, 64, 1), ("bsd_640x480_rf2_b8", 8, 120, 160, 2), ("720p", 1, 180, 320, 1),
+                              ("720p_b4", 4, 180, 320, 1)):
+        q = torch.randn(n, 128, h, w, device="cuda") * 0.2
+        pyr = [(torch.randn(n, 128, h, w, device="cuda") * 0.04, torch.randn(n, 64, 2 * h, 2 * w, device="cuda") * 0.04,
+                torch.randn(n, 32, 4 * h, 4 * w, device="cuda") * 0.04) for _ in range(rf)]
+        l3, l2, l1 = [p[0] for p in pyr], [p[1] for p in pyr], [p[2] for p in pyr]
+        args = (q, l3[0], l1[0], l2[0], l3[0]) if rf == 1 else (q, l3, l1, l2, l3)
+        with torch.no_grad():
+            ms = timed(lambda: st(*args), iters=5, warm=2)
+        flops = 2.0 * n * (h * w) * (rf * h * w) * 1152
+        out[name] = {"ms_module": ms, "relevance_TFLOPs_over_module_time": flops / (ms * 1e-3) / 1e12, "frames_per_s": n / (ms * 1e-3),
+                     "stats": st.last_stats.cpu().tolist()}
+        print("configs", name, out[name], flush=True)
+    selft = speinet_b200.SelfTransfer().cuda()
+    q = torch.randn(1, 128, 180, 320, device="cuda") * 0.2
+    with torch.no_grad():
+        out["selftransfer_720p_ms"] = timed(lambda: selft(q), iters=5, warm=2)
+    print("configs selftransfer", out["selftransfer_720p_ms"], flush=True)
+    REC["configs"] = out
+
+
 def stage_time720():
     lib = _lib.load()
     torch.manual_seed(0)
@@ -235,7 +299,7 @@ def main():
     t0 = time.time()
     fn = {"env": stage_env, "fold": stage_fold, "exact": lambda: stage_search(_lib.SEARCH_EXACT, "exact"),
           "tc": lambda: stage_search(_lib.SEARCH_TC, "tc"), "tile": stage_tile, "fuse": stage_fuse,
-          "time720": stage_time720}[a.stage]
+          "time720": stage_time720, "robust": stage_robust, "configs": stage_configs}[a.stage]
     try:
         fn()
         REC["ok"] = True
