@@ -88,7 +88,8 @@ gather_fold_kernel(const int32_t* __restrict__ arg, const float* __restrict__ re
 #pragma unroll
     for (int t = 0; t < 9; ++t)
       if ((valid >> t) & 1u) vadd(acc, v[t]);
-    *reinterpret_cast<V*>(obase + (size_t)c * out_plane) = fin<kTrueDiv>(acc);
+    // streaming (evict-first) store: the output is written once, the gathered reference should keep the L2
+    __stcs(reinterpret_cast<V*>(obase + (size_t)c * out_plane), fin<kTrueDiv>(acc));
   }
 }
 

@@ -444,6 +444,10 @@ int launch_relevance_tc(const Plan& p, char* ws, cudaStream_t st) {
   SPEI_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int), st));
   // per device, so set it on every launch (nn.DataParallel replicas call from several devices)
   SPEI_CUDA(cudaFuncSetAttribute(relevance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  // ask for the largest shared-memory carve-out: the persistent CTA uses ~137 KB of it and the rest lets
+  // kernels of other streams (rescoring / gather / fusion of the previous clip) co-reside on the SM
+  SPEI_CUDA(cudaFuncSetAttribute(relevance_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
   relevance_tc_kernel<<<p.G, kThreads, kSmemBytes, st>>>(tmq, tmk, t);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;

@@ -47,31 +47,34 @@ struct RescoreParams {
   int32_t* stats;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 rescore_kernel(const RescoreParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long wq = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // The kernel is latency bound (every phase is a dependent L2 round trip), so it is written for
+  // occupancy and early issue: the query's 9x128 patch goes to shared memory with cp.async (no register
+  // staging, <= 64 registers -> 32 warps per SM) and every load that does not depend on another is
+  // issued before the first branch.
+  __shared__ __align__(16) float qpatch[8][9 * kC3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long wq = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const int L = p.H * p.W;
   if (wq >= (long long)p.n * L) return;
   const int n = (int)(wq / L), ql = (int)(wq % L);
   const int y = ql / p.W, x = ql % p.W;
   const int lk1 = p.Hr * p.Wr;
 
-  // zero query patch: every relevance is 0 -> first index, S = 0 (reference semantics, SURVEY.md section 7.2)
+  // query patch -> shared memory (zero-filled taps outside the image)
   {
-    float s = 0.f;
-    const float* ss = p.qss + (size_t)n * L;
+    const float* qimg = p.q32 + (size_t)n * L * kC3;
+#pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) s += __ldg(ss + yy * p.W + xx);
+      const bool in = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const float* src = qimg + ((size_t)(in ? yy : y) * p.W + (in ? xx : x)) * kC3 + lane * 4;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&qpatch[warp][t * kC3 + lane * 4]);
+      const int sz = in ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
     }
-    if (s == 0.f) {
-      if (lane == 0) {
-        p.S[wq] = 0.f; p.arg32[wq] = 0;
-        if (p.arg64) p.arg64[wq] = 0;
-      }
-      return;
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // which query tile is this, and into how many key segments was it split?
@@ -80,13 +83,37 @@ rescore_kernel(const RescoreParams p) {
   const long long p0 = ((long long)n * p.QT + qt) * p.KT;
   const int nseg = (int)(cta_of_pair_d(p0 + p.KT - 1, p.P, p.G) - cta_of_pair_d(p0, p.P, p.G)) + 1;
   const int ncand = nseg * kTopK;
-  const float rq = __ldg(p.rq + wq);
   const float* cv = p.cval + (size_t)wq * p.maxseg * kTopK;
   const int32_t* ci = p.cidx + (size_t)wq * p.maxseg * kTopK;
 
+  // independent loads first: patch energy (zero test), query norm, first 32 candidates
+  float s = 0.f;
+  {
+    const float* ss = p.qss + (size_t)n * L;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) s += __ldg(ss + yy * p.W + xx);
+    }
+  }
+  const float rq = __ldg(p.rq + wq);
+  int j0 = -1;
+  float v0 = 0.f;
+  if (lane < ncand) { j0 = __ldg(ci + lane); v0 = __ldg(cv + lane); }
+
+  // zero query patch: every relevance is 0 -> first index, S = 0 (reference semantics, SURVEY.md section 7.2)
+  if (s == 0.f) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+      p.S[wq] = 0.f; p.arg32[wq] = 0;
+      if (p.arg64) p.arg64[wq] = 0;
+    }
+    return;
+  }
+
   // pass 1: best bf16 score
-  float bn = -INFINITY;
-  for (int e = lane; e < ncand; e += 32) {
+  float bn = j0 >= 0 ? v0 * rq : -INFINITY;
+  for (int e = lane + 32; e < ncand; e += 32) {
     const int j = __ldg(ci + e);
     if (j >= 0) bn = fmaxf(bn, __ldg(cv + e) * rq);
   }
@@ -100,6 +127,8 @@ rescore_kernel(const RescoreParams p) {
     const int e = sg * kTopK + (kTopK - 1);
     if (__ldg(ci + e) >= 0 && __ldg(cv + e) * rq >= thr) sat = true;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
   if (__any_sync(0xffffffffu, sat)) {
     if (lane == 0) {
       const int pos = atomicAdd(p.flag_count + n, 1);
@@ -108,17 +137,7 @@ rescore_kernel(const RescoreParams p) {
     }
     return;  // S / arg are written by unpack_kernel after the exhaustive search
   }
-
-  // the query's 9 x 128 patch, 4 channels per lane
-  float4 qv[9];
-  const float* qimg = p.q32 + (size_t)n * L * kC3;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    qv[t] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-                ? __ldg(reinterpret_cast<const float4*>(qimg + ((size_t)yy * p.W + xx) * kC3) + lane)
-                : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]) + lane;  // tap t at qv[t * 32]
 
   // pass 2: exact relevance of every kept candidate
   unsigned long long best = 0ull;
@@ -129,8 +148,8 @@ rescore_kernel(const RescoreParams p) {
     int j = -1;
     float vb = 0.f;
     if (e < ncand) {
-      j = __ldg(ci + e);
-      vb = __ldg(cv + e) * rq;
+      j = e0 == 0 ? j0 : __ldg(ci + e);
+      vb = (e0 == 0 ? v0 : __ldg(cv + e)) * rq;
       if (j >= 0 && !(vb >= thr)) j = -1;
     }
     unsigned m = __ballot_sync(0xffffffffu, j >= 0);
@@ -141,19 +160,21 @@ rescore_kernel(const RescoreParams p) {
       const float vbb = __shfl_sync(0xffffffffu, vb, src);
       const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
       const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // four independent chains (latency), fixed order
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
         if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
           const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
-          acc = fma((double)qv[t].x, (double)kv.x, acc);
-          acc = fma((double)qv[t].y, (double)kv.y, acc);
-          acc = fma((double)qv[t].z, (double)kv.z, acc);
-          acc = fma((double)qv[t].w, (double)kv.w, acc);
+          const float4 qq = qv[t * 32];
+          acc0 = fma((double)qq.x, (double)kv.x, acc0);
+          acc1 = fma((double)qq.y, (double)kv.y, acc1);
+          acc2 = fma((double)qq.z, (double)kv.z, acc2);
+          acc3 = fma((double)qq.w, (double)kv.w, acc3);
         }
       }
 #pragma unroll
+      double acc = (acc0 + acc1) + (acc2 + acc3);
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
       const float score = (float)(acc * (double)rq * (double)rk);
@@ -303,8 +324,9 @@ exact_search_kernel(const ExactParams p) {
 // queries are left to exact_search_kernel (which skips the others).
 constexpr int kSmallMax = 64;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 exact_small_kernel(const ExactParams p) {
+  __shared__ __align__(16) float qpatch[9 * kC3];
   const int n = blockIdx.z;
   const int cnt = __ldg(p.list_count + n);
   if (cnt == 0 || cnt > kSmallMax) return;
@@ -313,35 +335,39 @@ exact_small_kernel(const ExactParams p) {
   const int per = (Lk + gridDim.x - 1) / gridDim.x;
   const int k_lo = blockIdx.x * per, k_hi = min(Lk, k_lo + per);
   const float* qimg = p.q32 + (size_t)n * L * kC3;
+  const float4* qv = reinterpret_cast<const float4*>(qpatch) + lane;  // tap t at qv[t * 32]
   for (int qi = 0; qi < cnt; ++qi) {
     const int q = __ldg(p.list + (size_t)n * L + qi);
     const int y = q / p.W, x = q % p.W;
     const float rq = __ldg(p.rq + (size_t)n * L + q);
-    float4 qv[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
+    __syncthreads();  // previous query's patch no longer in use
+    for (int e = threadIdx.x; e < 9 * 32; e += 256) {
+      const int t = e >> 5, l4 = e & 31;
       const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      qv[t] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-                  ? __ldg(reinterpret_cast<const float4*>(qimg + ((size_t)yy * p.W + xx) * kC3) + lane)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool in = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      reinterpret_cast<float4*>(qpatch)[e] =
+          in ? __ldg(reinterpret_cast<const float4*>(qimg + ((size_t)yy * p.W + xx) * kC3) + l4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __syncthreads();
     unsigned long long best = 0ull;
     for (int j = k_lo + warp; j < k_hi; j += 8) {
       const int f = j / lk1, rem = j - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
       const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // four independent chains (latency), fixed order
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
         if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
           const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
-          acc = fma((double)qv[t].x, (double)kv.x, acc);
-          acc = fma((double)qv[t].y, (double)kv.y, acc);
-          acc = fma((double)qv[t].z, (double)kv.z, acc);
-          acc = fma((double)qv[t].w, (double)kv.w, acc);
+          const float4 qq = qv[t * 32];
+          acc0 = fma((double)qq.x, (double)kv.x, acc0);
+          acc1 = fma((double)qq.y, (double)kv.y, acc1);
+          acc2 = fma((double)qq.z, (double)kv.z, acc2);
+          acc3 = fma((double)qq.w, (double)kv.w, acc3);
         }
       }
 #pragma unroll
+      double acc = (acc0 + acc1) + (acc2 + acc3);
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
       const unsigned long long key = pack_score((float)(acc * (double)rq * (double)rk), j);
@@ -439,7 +465,7 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   e.key_splits = max_splits < 450 ? max_splits : 450;
   e.small_max = kSmallMax;
   const int key_blocks = (p.rf * p.Hr * p.Wr + 63) / 64;
-  exact_small_kernel<<<dim3(key_blocks < 592 ? key_blocks : 592, 1, p.n), 256, 0, st>>>(e);
+  exact_small_kernel<<<dim3(key_blocks < 592 ? key_blocks : 592, 1, p.n), 256, 0, st>>>(e);  // one wave at 4 blocks / SM
   SPEI_CUDA(cudaGetLastError());
   exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());

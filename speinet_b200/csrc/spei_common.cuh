@@ -18,7 +18,7 @@ constexpr int kQTileV = 16;       // query tile: 8 x 16 positions = 128 MMA rows
 constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA columns
 constexpr int kTopK = 8;          // bf16-pass candidates kept per query per key segment
 constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
-constexpr int kStages = 6;        // key pipeline depth
+constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight)
 
 // One operand (query set or key set) staged in (u, v) coordinates: u is the fast axis in memory.
 // orient 0: u = x, v = y.   orient 1: u = y, v = x (image transposed so the tile grid wastes less).

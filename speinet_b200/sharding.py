@@ -86,8 +86,9 @@ def gather_rows(parts, h: int, rank: int, world: int, group=None):
         per = max(((r + 1) * h // world - r * h // world) for r in range(world)) * s
         send = t.new_zeros(t.shape[:2] + (per,) + t.shape[3:])
         send[:, :, :t.shape[2]] = t
-        recv = t.new_empty((world,) + tuple(send.shape))
+        recv = t.new_empty((world * send.shape[0],) + tuple(send.shape[1:]))  # concatenated along dim 0 (gloo and NCCL)
         dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+        recv = recv.view((world,) + tuple(send.shape))
         for r in range(world):
             y0, y1 = r * h // world, (r + 1) * h // world
             full[:, :, y0 * s:y1 * s] = recv[r][:, :, :(y1 - y0) * s]
