@@ -173,8 +173,8 @@ rescore_kernel(const RescoreParams p) {
           acc3 = fma((double)qq.w, (double)kv.w, acc3);
         }
       }
-#pragma unroll
       double acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
       const float score = (float)(acc * (double)rq * (double)rk);
@@ -324,19 +324,20 @@ exact_search_kernel(const ExactParams p) {
 // queries are left to exact_search_kernel (which skips the others).
 constexpr int kSmallMax = 64;
 
+// grid: (key blocks, query lanes, n)
 __global__ void __launch_bounds__(256, 4)
 exact_small_kernel(const ExactParams p) {
   __shared__ __align__(16) float qpatch[9 * kC3];
   const int n = blockIdx.z;
   const int cnt = __ldg(p.list_count + n);
-  if (cnt == 0 || cnt > kSmallMax) return;
+  if (cnt == 0 || cnt > kSmallMax || (int)blockIdx.y >= cnt) return;
   const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = (Lk + gridDim.x - 1) / gridDim.x;
   const int k_lo = blockIdx.x * per, k_hi = min(Lk, k_lo + per);
   const float* qimg = p.q32 + (size_t)n * L * kC3;
   const float4* qv = reinterpret_cast<const float4*>(qpatch) + lane;  // tap t at qv[t * 32]
-  for (int qi = 0; qi < cnt; ++qi) {
+  for (int qi = blockIdx.y; qi < cnt; qi += gridDim.y) {
     const int q = __ldg(p.list + (size_t)n * L + qi);
     const int y = q / p.W, x = q % p.W;
     const float rq = __ldg(p.rq + (size_t)n * L + q);
@@ -353,24 +354,23 @@ exact_small_kernel(const ExactParams p) {
     for (int j = k_lo + warp; j < k_hi; j += 8) {
       const int f = j / lk1, rem = j - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
       const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // four independent chains (latency), fixed order
+      // fp32 accumulation like exact_search_kernel (the exhaustive paths agree with each other and are
+      // within ~1e-7 of the fp64 rescoring, far inside the 1e-5 near-tie rule)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
         if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
           const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
           const float4 qq = qv[t * 32];
-          acc0 = fma((double)qq.x, (double)kv.x, acc0);
-          acc1 = fma((double)qq.y, (double)kv.y, acc1);
-          acc2 = fma((double)qq.z, (double)kv.z, acc2);
-          acc3 = fma((double)qq.w, (double)kv.w, acc3);
+          a0 = fmaf(qq.x, kv.x, a0); a1 = fmaf(qq.y, kv.y, a1); a2 = fmaf(qq.z, kv.z, a2); a3 = fmaf(qq.w, kv.w, a3);
         }
       }
+      float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
-      double acc = (acc0 + acc1) + (acc2 + acc3);
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
-      const unsigned long long key = pack_score((float)(acc * (double)rq * (double)rk), j);
+      const unsigned long long key = pack_score(acc * rq * rk, j);
       best = key > best ? key : best;
     }
     if (lane == 0 && best) atomicMax(p.packed + (size_t)n * L + q, best);
@@ -465,7 +465,7 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   e.key_splits = max_splits < 450 ? max_splits : 450;
   e.small_max = kSmallMax;
   const int key_blocks = (p.rf * p.Hr * p.Wr + 63) / 64;
-  exact_small_kernel<<<dim3(key_blocks < 592 ? key_blocks : 592, 1, p.n), 256, 0, st>>>(e);  // one wave at 4 blocks / SM
+  exact_small_kernel<<<dim3(key_blocks < 296 ? key_blocks : 296, 8, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());
   exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());

@@ -225,6 +225,25 @@ def test_two_reference_frames_extension():
         assert np.array_equal(T1.cpu().numpy(), w1) and np.array_equal(T2.cpu().numpy(), w2) and np.array_equal(T3.cpu().numpy(), w3)
 
 
+def test_real_model_forward_features(golden):
+    """The boundary tensors of a real SPEINet forward (random-init weights; tests/golden/make_golden_model.py):
+    what the reference computed at speinet.py:135 and :93-109 vs. the CUDA path."""
+    g = golden("model_forward")
+    st = speinet_b200.SearchTransfer(fold_mode="cpu").cuda()
+    k = cu(g["ref_lv3"])
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(cu(g["q"]), k, cu(g["ref_lv1"]), cu(g["ref_lv2"]), k, return_index=True)
+        n_tie = assert_indices_agree(g["q"], g["ref_lv3"], arg.cpu().numpy(), g["arg"])
+        np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
+        if n_tie == 0:
+            assert np.array_equal(T3.cpu().numpy(), g["T_lv3"])
+            assert np.array_equal(T2.cpu().numpy(), g["T_lv2"])
+            assert np.array_equal(T1.cpu().numpy(), g["T_lv1"])
+        for lvl, scale, T in ((3, 1, T3), (2, 2, T2), (1, 4, T1)):
+            f = speinet_b200.fuse_level(cu(g[f"dec{lvl}"]), T, S, cu(g[f"w{lvl}"]), cu(g[f"b{lvl}"]), scale)
+            np.testing.assert_allclose(f.cpu().numpy(), g[f"f{lvl}"], rtol=1e-4, atol=1e-6)
+
+
 def test_bf16_inputs_within_1e2():
     rng = np.random.default_rng(21)
     h, w = 16, 24

@@ -114,6 +114,22 @@ def test_fusion_matches_reference(golden):
         np.testing.assert_allclose(f, g[f"f{lvl}"], rtol=1e-4, atol=1e-6)
 
 
+def test_oracle_on_real_model_forward(golden):
+    """Features captured from a real SPEINet forward (tests/golden/make_golden_model.py): the oracle
+    reproduces what crossed the hot-path boundary at speinet.py:135 and the fused features of :94/:97/:109."""
+    g = golden("model_forward")
+    S, T3, T2, T1, arg, _ = oracle.search_transfer(g["q"], g["ref_lv3"], g["ref_lv1"], g["ref_lv2"], g["ref_lv3"])
+    agree, _, n_tie = oracle.near_tie_agreement(g["q"], g["ref_lv3"], arg, g["arg"])
+    assert agree.all()
+    np.testing.assert_allclose(S, g["S"], rtol=1e-4, atol=1e-6)
+    if n_tie == 0:
+        assert np.array_equal(T3, g["T_lv3"]) and np.array_equal(T2, g["T_lv2"]) and np.array_equal(T1, g["T_lv1"])
+    assert np.array_equal(g["dec3"], g["q"])                    # speinet.py:93: the lv3 decoder feature is f_fusion itself
+    for lvl, scale in ((3, 1), (2, 2), (1, 4)):
+        f = oracle.fuse_level(g[f"dec{lvl}"], g[f"T_lv{lvl}"], g["S"], g[f"w{lvl}"], g[f"b{lvl}"], scale)
+        np.testing.assert_allclose(f, g[f"f{lvl}"], rtol=1e-4, atol=1e-6)
+
+
 def test_torch_port_matches_golden(golden):
     import torch
     from oracle.torch_port import search_transfer_torch, fuse_level_torch
