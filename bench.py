@@ -35,7 +35,7 @@ import torch  # noqa: E402
 H, W, C3 = 180, 320, 128                      # lv3 grid of a 1280x720 frame (speinet.py:124-127)
 L = H * W
 FLOPS_RELEVANCE = 2.0 * L * L * 9 * C3        # 7.644 TFLOP
-KERNELS_PER_STEP = 2 + 3 + 1 + 5 + 3 + 3      # stage q, stage k, tcgen05, rescore group, gather/fold x3, fuse x3
+KERNELS_PER_STEP = 2 + 3 + 1 + 5 + 4 + 3      # stage q, stage k, tcgen05, rescore group, gather/fold x3 (+ lv2 staging), fuse x3
 WORKLOAD = "searchtransfer_fusion_1280x720_1ref"
 
 
@@ -243,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
         w = wsps[i & 1]
         chk(lib.spei_rescore(sref, vp(S), vp(arg32), ctypes.c_void_p(0), vp(stats), w, nbytes.value, st_handle), "rescore")
         for lvl in (3, 2, 1):
-            chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), st_handle), "gather_fold")
+            chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), vp(k5), w, nbytes.value, st_handle), "gather_fold")
         for lvl in (3, 2, 1):
             c = T[lvl].shape[1]
             chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
@@ -315,7 +315,8 @@ def run_ours(args, rank, world, local_rank):
     secondary.append({"stage": "a_stage_norm(q+k)", "ms": t, "bytes": stage_bytes})
     for lvl in (3, 2, 1):
         nb = 2 * T[lvl].numel() * 4                   # written once + at most the same amount read
-        t = timed_ms(lambda: chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), stream), "gather_fold"))
+        t = timed_ms(lambda: chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), vp(k5), wsp, nbytes.value, stream),
+                                 "gather_fold"))
         secondary.append({"stage": f"c_gather_fold_lv{lvl}", "ms": t, "bytes": nb})
     for lvl in (3, 2, 1):
         c = T[lvl].shape[1]

@@ -104,9 +104,12 @@ int spei_rescore(const SpeiShape *shape, float *S, int32_t *arg32, int64_t *arg6
 
 /* (c) unfold(ref) + bis gather + fold + /9 of one pyramid level (SearchTransfer.py:36-46),
  * level = 3, 2 or 1; ref is [n, rf, c, s*hr, s*wr], out is [n, c, s*h, s*w], s = 1, 2, 4.
- * `arg32` is [n, h*w] int32 key indices (any values in [0, rf*hr*wr)). */
+ * `arg32` is [n, h*w] int32 key indices (any values in [0, rf*hr*wr)).
+ * lv3 / lv2 gather from a channels-last copy kept in `workspace`; `staged_k` is the refsr_lv3 pointer
+ * last given to spei_stage_norm with this workspace (or NULL): when `ref == staged_k` at level 3 the copy
+ * made there is reused (ref_lv3 and refsr_lv3 are the same tensor at speinet.py:135). */
 int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, const float *ref, float *out,
-                     void *stream);
+                     const float *staged_k, void *workspace, size_t workspace_bytes, void *stream);
 
 /* (d) one fusion line of SPEINet._decode (speinet.py:93-94 / 96-97 / 108-109):
  *   out = dec + (W . cat(dec, t) + b) * bicubic_up(S, scale),  scale in {1,2,4}

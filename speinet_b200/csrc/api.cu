@@ -87,6 +87,8 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.off_arg32 = take(nq * L * 4);
   p.off_counters = take((nq + 16) * 4);  // per-item count of queries queued for the exhaustive search
   p.off_errflag = take(64);
+  p.off_ref3n = take(nk * Lk1 * kC3 * 4);        // channels-last copies of ref_lv3 (when it is not the searched tensor)
+  p.off_ref2n = take(nk * Lk1 * 4 * (kC3 / 2) * 4);  // ... and of ref_lv2 ([2hr][2wr][64])
   p.total = off;
   *out = p;
   return SPEI_OK;
@@ -245,18 +247,37 @@ int spei_plan_info(const SpeiShape* shape, int32_t* out16) {
   return SPEI_OK;
 }
 
-int spei_gather_fold(const SpeiShape* shape, int level, const int32_t* arg32, const float* ref, float* out,
-                     void* stream) {
-  int rc = check_shape(shape);
-  if (rc) return rc;
-  int sms = 0;
-  if ((rc = check_device(&sms))) return rc;
-  if (level < 1 || level > 3) { set_error("level must be 1, 2 or 3 (got %d)", level); return SPEI_ERR_ARG; }
-  if ((rc = check_ptr(arg32, "arg32", 4)) || (rc = check_ptr(ref, "ref", 16)) || (rc = check_ptr(out, "out", 16))) return rc;
+// One pyramid level of the transfer.  lv1 (32 channels, 16-byte runs already) gathers straight from the
+// planar input; lv3 / lv2 gather from a channels-last copy (512-byte runs), which for lv3 is the fp32 copy
+// spei_stage_norm already made whenever ref_lv3 is the searched tensor itself (speinet.py:135).
+static int gather_level(const Plan& p, const SpeiShape* shape, int level, const int32_t* arg32, const float* ref, float* out,
+                        const float* staged_k, char* ws, cudaStream_t st) {
   const int scale = level == 3 ? 1 : (level == 2 ? 2 : 4);
   const int c = level == 3 ? shape->c3 : (level == 2 ? shape->c2 : shape->c1);
-  return launch_gather_fold(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode,
-                            arg32, ref, out, (cudaStream_t)stream);
+  if (level == 1)
+    return launch_gather_fold(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode, arg32, ref,
+                              out, st);
+  const float* src;
+  if (level == 3 && staged_k != nullptr && ref == staged_k) {
+    src = (const float*)(ws + p.off_k32);
+  } else {
+    float* dst = (float*)(ws + (level == 3 ? p.off_ref3n : p.off_ref2n));
+    int rc = launch_stage_ref_nhwc(ref, shape->n * shape->rf, c, scale * shape->hr, scale * shape->wr, dst, st);
+    if (rc) return rc;
+    src = dst;
+  }
+  return launch_gather_fold_nhwc(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode, arg32, src,
+                                 out, st);
+}
+
+int spei_gather_fold(const SpeiShape* shape, int level, const int32_t* arg32, const float* ref, float* out, const float* staged_k,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  Plan p;
+  int rc = prepare(shape, workspace, workspace_bytes, &p);
+  if (rc) return rc;
+  if (level < 1 || level > 3) { set_error("level must be 1, 2 or 3 (got %d)", level); return SPEI_ERR_ARG; }
+  if ((rc = check_ptr(arg32, "arg32", 4)) || (rc = check_ptr(ref, "ref", 16)) || (rc = check_ptr(out, "out", 16))) return rc;
+  return gather_level(p, shape, level, arg32, ref, out, staged_k, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const float* dec, const float* t,
@@ -294,14 +315,12 @@ int spei_search_transfer(const SpeiShape* shape, const float* q, const float* k,
   // (b) SearchTransfer.py:33-34
   if ((rc = spei_relevance_argmax(shape, S, arg32, arg, stats, workspace, workspace_bytes, stream))) return rc;
   // (c) SearchTransfer.py:36-46
-  struct Lvl { const float* ref; float* out; int c, scale; };
-  const Lvl lv[3] = {{ref3, T3, shape->c3, 1}, {ref2, T2, shape->c2, 2}, {ref1, T1, shape->c1, 4}};
+  struct Lvl { const float* ref; float* out; int level; };
+  const Lvl lv[3] = {{ref3, T3, 3}, {ref2, T2, 2}, {ref1, T1, 1}};
   for (const Lvl& l : lv) {
     if (!l.ref) continue;
     if ((rc = check_ptr(l.ref, "ref", 16)) || (rc = check_ptr(l.out, "T", 16))) return rc;
-    if ((rc = launch_gather_fold(shape->n, shape->rf, l.c, shape->h, shape->w, shape->hr, shape->wr, l.scale,
-                                 shape->fold_mode, arg32, l.ref, l.out, st)))
-      return rc;
+    if ((rc = gather_level(p, shape, l.level, arg32, l.ref, l.out, k, ws, st))) return rc;
   }
   return SPEI_OK;
 }

@@ -37,57 +37,69 @@ __device__ __forceinline__ float vzero(float) { return 0.f; }
 __device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); }
 __device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+__device__ const float4 g_zero16 = {0.f, 0.f, 0.f, 0.f};  // source of every non-contributing neighbour
+
 // grid: (ceil(W/32), S*H, n)   block: (32 cells, 8 channel lanes)
 template <int S, bool kCpuOrder, bool kTrueDiv>
 __global__ void __launch_bounds__(256)
 gather_fold_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
                    int H, int W, int Hr, int Wr) {
   using V = typename Vec<S>::T;
-  const int X = blockIdx.x * 32 + threadIdx.x;
+  __shared__ long long s_off[9][32];  // per (neighbour, cell): float offset of the source run, -1 = no contribution
+  const int X0 = blockIdx.x * 32, X = X0 + threadIdx.x;
   const int y = blockIdx.y, n = blockIdx.z;
-  if (X >= W) return;
   const int Y = y / S;
   const int lk1 = Hr * Wr, jmax = rf * lk1 - 1;
   const size_t ref_plane = (size_t)(S * Hr) * (S * Wr);  // one channel of one reference frame
   const int ref_pitch = S * Wr;
 
-  // decode the <=9 neighbours once; offsets are in floats relative to channel 0 of frame f
-  long long off[9];
-  unsigned valid = 0;
+  // decode the <=9 neighbours of the block's 32 cells ONCE, cooperatively (288 decodes over 256 threads);
+  // the integer divisions of the index decode would otherwise dominate the instruction count of every thread
   const int32_t* a = arg + (size_t)n * H * W;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
+  for (int e = threadIdx.y * 32 + threadIdx.x; e < 9 * 32; e += 256) {
+    const int t = e >> 5, cell = e & 31;
     // CUDA col2im order: ascending (h_col, w_col); CPU order: ascending (ki,kj) = descending origin
     const int tt = kCpuOrder ? 8 - t : t;
     const int dy = tt / 3 - 1, dx = tt % 3 - 1;
-    const int qy = Y + dy, qx = X + dx;
-    off[t] = 0;
-    if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+    const int Xc = X0 + cell, qy = Y + dy, qx = Xc + dx;
+    long long o = -1;
+    if (Xc < W && qy >= 0 && qy < H && qx >= 0 && qx < W) {
       int j = __ldg(a + qy * W + qx);
       j = min(max(j, 0), jmax);
       const int f = j / lk1, rem = j - f * lk1;
       const int hr = rem / Wr, wr = rem - hr * Wr;
-      const int cy = Y + hr - qy, cx = X + wr - qx;  // source cell
-      if (cy >= 0 && cy < Hr && cx >= 0 && cx < Wr) {
-        valid |= 1u << t;
-        off[t] = (long long)f * C * (long long)ref_plane + (long long)(cy * S + (y - Y * S)) * ref_pitch + (long long)cx * S;
-      }
+      const int cy = Y + hr - qy, cx = Xc + wr - qx;  // source cell
+      if (cy >= 0 && cy < Hr && cx >= 0 && cx < Wr)
+        o = (long long)f * C * (long long)ref_plane + (long long)(cy * S + (y - Y * S)) * ref_pitch + (long long)cx * S;
     }
+    s_off[t][cell] = o;
   }
+  __syncthreads();
+  if (X >= W) return;
+  // Branch-free inner loop: a neighbour without a contribution reads a 16-byte zero constant with channel
+  // stride 0 (adding +0.0f never changes an fp32 sum that started at +0.0f), so the 9 loads and 9 adds per
+  // channel carry no predicates and the per-channel address is one multiply-add.
   const float* rbase = ref + (size_t)n * rf * C * ref_plane;
+  const float* base[9];
+  unsigned step[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const long long o = s_off[t][threadIdx.x];
+    base[t] = o >= 0 ? rbase + o : reinterpret_cast<const float*>(&g_zero16);
+    step[t] = o >= 0 ? (unsigned)ref_plane : 0u;
+  }
   const size_t out_plane = (size_t)(S * H) * (S * W);
   float* obase = out + (size_t)n * C * out_plane + (size_t)y * (S * W) + (size_t)X * S;
   const int cpt = C / 8;
+#pragma unroll 2
   for (int ci = 0; ci < cpt; ++ci) {
-    const int c = threadIdx.y * cpt + ci;
-    const float* rc = rbase + (size_t)c * ref_plane;
+    const unsigned c = threadIdx.y * cpt + ci;
     V v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = (valid >> t) & 1u ? __ldg(reinterpret_cast<const V*>(rc + off[t])) : vzero(V{});
+    for (int t = 0; t < 9; ++t) v[t] = __ldg(reinterpret_cast<const V*>(base[t] + (size_t)c * step[t]));
     V acc = vzero(V{});
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-      if ((valid >> t) & 1u) vadd(acc, v[t]);
+    for (int t = 0; t < 9; ++t) vadd(acc, v[t]);
     // streaming (evict-first) store: the output is written once, the gathered reference should keep the L2
     __stcs(reinterpret_cast<V*>(obase + (size_t)c * out_plane), fin<kTrueDiv>(acc));
   }

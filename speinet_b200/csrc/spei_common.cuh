@@ -42,7 +42,7 @@ struct Plan {
   int maxseg;      // max key segments a query tile is split into
   // workspace offsets (bytes)
   size_t off_qbf, off_kbf, off_q32, off_k32, off_rq, off_rk, off_rkpad, off_qss, off_kss;
-  size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag;
+  size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag, off_ref3n, off_ref2n;
   size_t total;
 };
 
@@ -66,6 +66,9 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
 int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, char* ws, cudaStream_t st);
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
                        const int32_t* arg32, const float* ref, float* out, cudaStream_t st);
+int launch_stage_ref_nhwc(const float* ref, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st);
+int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
+                            const int32_t* arg32, const float* ref_nhwc, float* out, cudaStream_t st);
 int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
                       const float* weight, const float* bias, float* out, cudaStream_t st);
 

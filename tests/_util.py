@@ -108,6 +108,8 @@ def gather_fold(arg32, ref, level, n, h, w, hr, wr, rf, fold_mode):
     s = {3: 1, 2: 2, 1: 4}[level]
     c = ref.shape[2]
     out = torch.empty((n, c, s * h, s * w), device="cuda")
-    _lib.check(lib.spei_gather_fold(ctypes.byref(shape), level, vp(arg32), vp(ref), vp(out), cur_stream()), "gather_fold")
+    ws, ptr, nbytes = alloc_workspace(shape)
+    _lib.check(lib.spei_gather_fold(ctypes.byref(shape), level, vp(arg32), vp(ref), vp(out), ctypes.c_void_p(0),
+                                    ctypes.c_void_p(ptr), nbytes, cur_stream()), "gather_fold")
     torch.cuda.synchronize()
     return out

@@ -210,6 +210,33 @@ def stage_robust():
     REC["robust"] = out
 
 
+def stage_gather():
+    """Gather/fold at 720p for a random match field (randn features), a smooth one (identity + small
+    jitter, what real video gives) and the identity: time per level and achieved bytes/s."""
+    lib = _lib.load()
+    torch.manual_seed(8)
+    h, w = 180, 320
+    shape = U.make_shape(1, h, w, h, w)
+    st = U.cur_stream()
+    ws, wsp, nbytes = U.alloc_workspace(shape)
+    ident = torch.arange(h * w, device="cuda", dtype=torch.int64)
+    yy, xx = ident // w, ident % w
+    jit = lambda m: torch.randint(-m, m + 1, (h * w,), device="cuda")
+    smooth = ((yy + jit(2)).clamp(0, h - 1) * w + (xx + jit(2)).clamp(0, w - 1)).to(torch.int32)[None].contiguous()
+    fields = {"random": torch.randint(0, h * w, (1, h * w), device="cuda", dtype=torch.int32), "smooth_jitter2": smooth,
+              "identity": ident.to(torch.int32)[None].contiguous()}
+    out = {}
+    for lvl, c, s in ((3, 128, 1), (2, 64, 2), (1, 32, 4)):
+        ref = torch.randn(1, 1, c, s * h, s * w, device="cuda")
+        o1 = torch.empty(1, c, s * h, s * w, device="cuda")
+        for name, arg in fields.items():
+            t1 = timed(lambda: _lib.check(lib.spei_gather_fold(ctypes.byref(shape), lvl, U.vp(arg), U.vp(ref), U.vp(o1), ctypes.c_void_p(0),
+                                                                ctypes.c_void_p(wsp), nbytes, st), "gf"), iters=10)
+            out[f"lv{lvl}_{name}"] = {"us": t1 * 1e3, "GBs_read_plus_write": 2 * o1.numel() * 4 / (t1 * 1e-3) / 1e9}
+            print("gather", f"lv{lvl}_{name}", out[f"lv{lvl}_{name}"], flush=True)
+    REC["gather"] = out
+
+
 def stage_configs():
     """The other BASELINE.json configs through the public module: 256x256 (64x64 grid), BSD 640x480 with two
     sharp frames and batch 8 (configs[3]), 720p SelfTransfer; module-level time incl. host overhead."""
@@ -267,7 +294,8 @@ def stage_time720():
     for lvl, ref in ((3, k), (2, r2), (1, r1)):
         sc = {3: 1, 2: 2, 1: 4}[lvl]
         out = torch.empty(1, ref.shape[2], sc * h, sc * w, device="cuda")
-        t = timed(lambda: _lib.check(lib.spei_gather_fold(ctypes.byref(shape), lvl, U.vp(arg32), U.vp(ref), U.vp(out), st), "gf"))
+        t = timed(lambda: _lib.check(lib.spei_gather_fold(ctypes.byref(shape), lvl, U.vp(arg32), U.vp(ref), U.vp(out), U.vp(k) if lvl == 3 else ctypes.c_void_p(0),
+                                                            wsp, nbytes, st), "gf"))
         REC[f"ms_gather_fold_lv{lvl}"] = t
         REC[f"GBs_gather_fold_lv{lvl}"] = 2 * out.numel() * 4 / (t * 1e-3) / 1e9
     from speinet_b200 import fuse_level
@@ -299,7 +327,7 @@ def main():
     t0 = time.time()
     fn = {"env": stage_env, "fold": stage_fold, "exact": lambda: stage_search(_lib.SEARCH_EXACT, "exact"),
           "tc": lambda: stage_search(_lib.SEARCH_TC, "tc"), "tile": stage_tile, "fuse": stage_fuse,
-          "time720": stage_time720, "robust": stage_robust, "configs": stage_configs}[a.stage]
+          "time720": stage_time720, "robust": stage_robust, "configs": stage_configs, "gather": stage_gather}[a.stage]
     try:
         fn()
         REC["ok"] = True
