@@ -136,9 +136,12 @@ def test_gather_fold_bit_exact_given_reference_indices(golden, name):
         assert torch.equal(got, want), f"lv{lvl}: CUDA-order fold differs from torch CUDA F.fold"
 
 
-def test_gather_fold_multi_frame_and_oracle_closed_form():
+@pytest.mark.parametrize("dims", [(2, 11, 13, 9, 17, 2), (1, 5, 70, 6, 45, 1), (1, 3, 33, 40, 3, 3)])
+def test_gather_fold_multi_frame_and_oracle_closed_form(dims):
+    """Ragged grids (query grid != reference grid, widths across the 32-cell block boundary), several
+    reference frames, arbitrary (not argmax) indices: every level against the oracle's closed form."""
     rng = np.random.default_rng(4)
-    n, h, w, hr, wr, rf = 2, 11, 13, 9, 17, 2
+    n, h, w, hr, wr, rf = dims
     arg = rng.integers(0, rf * hr * wr, size=(n, h * w)).astype(np.int32)
     for lvl, c, s in ((3, 128, 1), (2, 64, 2), (1, 32, 4)):
         refs = [rng.standard_normal((n, c, s * hr, s * wr)).astype(np.float32) for _ in range(rf)]
