@@ -346,13 +346,16 @@ def run_ours(args, rank, world, local_rank):
             dist.all_gather_into_tensor(frame_out, Fo[1][:, :3].contiguous())
         torch.cuda.synchronize(dev)
 
-    e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(n_e2e)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_check = float((out_sets[(n_e2e - 1) & 1]["f1"] - Fo[1].cpu()).abs().max())  # same inputs -> same fused features
+    if args.no_e2e:
+        n_e2e, e2e_s, e2e_check = 0, 1.0, None
+    else:
+        e2e_run(3)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(n_e2e)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_check = float((out_sets[(n_e2e - 1) & 1]["f1"] - Fo[1].cpu()).abs().max())  # same inputs -> same fused features
     clocks = sampler.stop()
 
     t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
@@ -401,6 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs only; not a valid bench line)")
     ap.add_argument("--overlap", action="store_true", help="two-stream pipeline across consecutive clips (see run_ours)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

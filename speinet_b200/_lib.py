@@ -9,7 +9,9 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libspeinet_b200.so")
+# SPEINET_B200_LIB selects an alternative build of the same library (A/B kernel experiments, tools/ab_*.sh);
+# it is still this repo's CUDA library -- there is no other implementation to fall back to.
+LIB_PATH = os.environ.get("SPEINET_B200_LIB") or os.path.join(_PKG, "libspeinet_b200.so")
 
 FOLD_CUDA, FOLD_CPU = 0, 3
 FOLD_ORDER_CPU, FOLD_TRUE_DIV = 1, 2

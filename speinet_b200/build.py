@@ -43,19 +43,56 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_link(out: str, defines, objdir: str):
+    """Compile every .cu to an object in parallel (one nvcc each), then link the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-D{d}" for d in defines]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        res = subprocess.run([nvcc] + cflags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(one, sources()))
+    log = "".join(r.stdout + r.stderr for _, r in results)
+    if any(r.returncode != 0 for _, r in results):
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed while compiling " + ", ".join(os.path.basename(o) for o, r in results if r.returncode != 0))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [o for o, _ in results],
+                         capture_output=True, text=True)
+    log += res.stdout + res.stderr
+    if res.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc link failed")
+    return log
+
+
+def build_variant(out: str, defines, verbose: bool = False) -> str:
+    """An A/B build of the same sources with extra -D defines (e.g. SPEI_TOPK=8) into `out`;
+    select it at run time with SPEINET_B200_LIB=<out>."""
+    log = _compile_link(out, defines, os.path.join(PKG, "build", "obj_" + os.path.basename(out)))
+    if verbose:
+        sys.stderr.write(log)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+    log = _compile_link(LIB, [], os.path.join(PKG, "build", "obj"))
+    if verbose:
+        sys.stderr.write(log)
     with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
+        f.write(log)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:  # python -m speinet_b200.build --variant out.so SPEI_TOPK=8 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(os.path.abspath(sys.argv[i + 1]), sys.argv[i + 2:], verbose=True))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -184,7 +184,7 @@ int spei_relevance_candidates(const SpeiShape* shape, void* workspace, size_t wo
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
   if (rc) return rc;
-  return launch_relevance_tc(p, (char*)workspace, (cudaStream_t)stream);
+  return launch_relevance_tc(p, shape->eps > 0.f ? shape->eps : 2e-3f, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_rescore(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, void* workspace,
@@ -208,9 +208,9 @@ int spei_relevance_argmax(const SpeiShape* shape, float* S, int32_t* arg32, int6
   char* ws = (char*)workspace;
   if (stats) SPEI_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
   if (shape->search == SPEI_SEARCH_EXACT) return launch_exact_all(p, S, arg32, arg64, ws, st);
-  rc = launch_relevance_tc(p, ws, st);
-  if (rc) return rc;
   const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  rc = launch_relevance_tc(p, eps, ws, st);
+  if (rc) return rc;
   return launch_rescore(p, eps, S, arg32, arg64, stats, ws, st);
 }
 
@@ -220,7 +220,7 @@ int spei_debug_relevance_tile(const SpeiShape* shape, float* acc_out, void* work
   if (rc) return rc;
   if ((rc = check_ptr(acc_out, "acc_out", 16))) return rc;
   set_debug_acc(acc_out);
-  return launch_relevance_tc(p, (char*)workspace, (cudaStream_t)stream);
+  return launch_relevance_tc(p, shape->eps > 0.f ? shape->eps : 2e-3f, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_debug_error_flag(const SpeiShape* shape, void* workspace, size_t workspace_bytes, void* stream, int32_t* host_out) {

@@ -53,6 +53,8 @@ struct TcParams {
   int q_tu, q_orient, Uq, Vq, W, L;
   int k_tu, k_tiles_img, k_orient, Ny, Wr, lk1, UkT, VkT;
   uint32_t idesc, stage_bytes, k_lbo;
+  float win;         // candidate window (normalised relevance units, slightly wider than the rescoring's eps)
+  const float* rq;   // query reciprocal patch norms [n*L]: the epilogue's scores lack this factor
   const float* rkpad;
   float* cval;
   int32_t* cidx;
@@ -262,6 +264,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     int ti[kTopK];
     uint32_t tile_i = 0;
     long long qlin = -1;
+    float winq = 0.f;  // the window in this query's un-normalised score units
     float* rk_s = reinterpret_cast<float*>(smem + kRkSmemOffset) + ew * kAccCols;  // this warp's copy of the tile's key norms
     const int nchunk = p.Ny / 2;
     // key-norm prefetch: lane l owns float4 #l and #(l+32) of the tile's [Ny][8] reciprocal norms
@@ -286,6 +289,10 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
         const int u = qtu * kTileU + (m & 7), v = qtv * kQTileV + (m >> 3);
         qlin = (u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
+        winq = qlin >= 0 ? p.win / __ldg(p.rq + qlin) : 0.f;
+#ifdef SPEI_NO_WINDOW  // A/B only: plain top-k insertion
+        winq = INFINITY;
+#endif
       }
       const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
       const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
@@ -325,10 +332,13 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (r2 + 1 < nchunk) tc_ld16(taddr + (r2 + 1) * 16, a);  // v[] holds this chunk; refill a[] asynchronously
         float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
         mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]))));
-        if (mx > tv[kTopK - 1]) {
-          // compact slow path (taken by ~1 chunk in 4 per warp at 720p): bit mask of the qualifying
-          // columns, then one sorted insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
-          const float thr = tv[kTopK - 1];
+        // A score can only matter to the rescoring if it is within `win` of the best score seen so far
+        // (the final best is no smaller), so the entry bar is max(k-th best, best - win): once the
+        // running best has settled almost nothing passes it, whatever kTopK is.
+        const float thr = fmaxf(tv[kTopK - 1], tv[0] - winq);
+        if (mx > thr) {
+          // compact slow path: bit mask of the qualifying columns, then one sorted insertion per set
+          // bit.  Strict '>' keeps earlier keys ahead on ties.
           unsigned msk = 0;
 #pragma unroll
           for (int i = 0; i < 16; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
@@ -344,7 +354,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 2; ++j) s2[j] = (i & 4) ? s4[2 * j + 1] : s4[2 * j];
             float x = (i & 8) ? s2[1] : s2[0];
-            if (x > tv[kTopK - 1]) {
+            if (x > fmaxf(tv[kTopK - 1], tv[0] - winq)) {
               const int ku = ku0 + (i & 7), kv = kv0 + 2 * r2 + (i >> 3);
               int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku, kv, p.Wr);
 #pragma unroll
@@ -367,8 +377,11 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           const int slot = b - (int)(((p0 + 1) * (long long)p.G - 1) / p.P);
           float4* dv = reinterpret_cast<float4*>(p.cval + ((size_t)qlin * p.maxseg + slot) * kTopK);
           int4* di = reinterpret_cast<int4*>(p.cidx + ((size_t)qlin * p.maxseg + slot) * kTopK);
-          dv[0] = make_float4(tv[0], tv[1], tv[2], tv[3]); dv[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
-          di[0] = make_int4(ti[0], ti[1], ti[2], ti[3]); di[1] = make_int4(ti[4], ti[5], ti[6], ti[7]);
+#pragma unroll
+          for (int s4 = 0; s4 < kTopK / 4; ++s4) {
+            dv[s4] = make_float4(tv[4 * s4], tv[4 * s4 + 1], tv[4 * s4 + 2], tv[4 * s4 + 3]);
+            di[s4] = make_int4(ti[4 * s4], ti[4 * s4 + 1], ti[4 * s4 + 2], ti[4 * s4 + 3]);
+          }
         }
       }
     }
@@ -416,7 +429,7 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* tm, void* base, int nimg, co
 
 static thread_local float* tl_debug_acc = nullptr;  // set by spei_debug_relevance_tile for the next launch
 
-int launch_relevance_tc(const Plan& p, char* ws, cudaStream_t st) {
+int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
@@ -435,6 +448,8 @@ int launch_relevance_tc(const Plan& p, char* ws, cudaStream_t st) {
   t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
   t.k_lbo = (uint32_t)(p.k.tile_v + 2) * kRowBytes;
   t.stage_bytes = kCGS * t.k_lbo;
+  t.win = eps * 1.02f;  // a hair wider than the rescoring window: the two sides round differently
+  t.rq = (const float*)(ws + p.off_rq);
   t.rkpad = (const float*)(ws + p.off_rkpad);
   t.cval = (float*)(ws + p.off_cval);
   t.cidx = (int32_t*)(ws + p.off_cidx);

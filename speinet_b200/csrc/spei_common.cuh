@@ -16,7 +16,10 @@ constexpr int kCG = kC3 / 8;      // 16 channel groups of 8 bf16 = 16 bytes
 constexpr int kTileU = 8;         // tile extent along the fast (contiguous) image axis, both operands
 constexpr int kQTileV = 16;       // query tile: 8 x 16 positions = 128 MMA rows
 constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA columns
-constexpr int kTopK = 8;          // bf16-pass candidates kept per query per key segment
+#ifndef SPEI_TOPK
+#define SPEI_TOPK 16
+#endif
+constexpr int kTopK = SPEI_TOPK;  // bf16-pass candidates kept per query per key segment (multiple of 4)
 constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
 constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight)
 
@@ -59,7 +62,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // ---- stage launchers (defined in the .cu files) -----------------------------------------------
 int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st);
-int launch_relevance_tc(const Plan& p, char* ws, cudaStream_t st);
+int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st);
 void set_debug_acc(float* ptr);
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st);
