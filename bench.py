@@ -198,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
     wts = {l: (c.weight.detach().reshape(c.weight.shape[0], -1).contiguous(), c.bias.detach().contiguous()) for l, c in convs.items()}
 
     shape = _lib.SpeiShape(n=1, h=H, w=W, hr=H, wr=W, rf=1, c3=C3, c2=C3 // 2, c1=C3 // 4, fold_mode=_lib.FOLD_CUDA,
-                           search=_lib.SEARCH_TC, eps=0.0)
+                           search={"tc": _lib.SEARCH_TC, "tcs": _lib.SEARCH_TCS}[args.search], eps=0.0)
     nbytes = ctypes.c_size_t(0)
     _lib.check(lib.spei_workspace_bytes(ctypes.byref(shape), ctypes.byref(nbytes)), "workspace_bytes")
     ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
@@ -404,6 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search", default="tc", choices=["tc", "tcs"], help="tcgen05 candidate pass: dense 9-tap MMA or tap-sharing")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs only; not a valid bench line)")
     ap.add_argument("--overlap", action="store_true", help="two-stream pipeline across consecutive clips (see run_ours)")
     args = ap.parse_args()

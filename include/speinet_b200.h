@@ -41,6 +41,10 @@ extern "C" {
 /* relevance engine */
 #define SPEI_SEARCH_TC 0    /* tcgen05 bf16 candidate pass + exact fp32 rescoring (default)  */
 #define SPEI_SEARCH_EXACT 1 /* fp32 CUDA-core exhaustive search (checker / debugging)        */
+#define SPEI_SEARCH_TCS 2   /* tcgen05 bf16 candidate pass with tap sharing: the MMA contracts channels x the 3 taps
+                               along one image axis (K = 384), the epilogue adds the 3 taps along the other axis from
+                               neighbouring accumulator entries -- 2.3x fewer tensor-core flops for the same scores;
+                               same exact fp32 rescoring behind it                               */
 
 /* Problem description.  The reference instantiates c3=128, c2=64, c1=32 (n_feat=32,
  * speinet.py:53); lv2 / lv1 tensors are 2x / 4x the lv3 grids (SearchTransfer.py:36-38,44-46). */

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SPEINET_B200_LIB") or os.path.join(_PKG, "libspeinet_
 
 FOLD_CUDA, FOLD_CPU = 0, 3
 FOLD_ORDER_CPU, FOLD_TRUE_DIV = 1, 2
-SEARCH_TC, SEARCH_EXACT = 0, 1
+SEARCH_TC, SEARCH_EXACT, SEARCH_TCS = 0, 1, 2
 
 
 class SpeiShape(ctypes.Structure):

@@ -27,27 +27,33 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Pick the orientation (and, for keys, the tile height Ny) that wastes the fewest padded positions.
-static OperandPlan plan_operand(int H, int W, bool is_key) {
+// dense:       tiles are 8 (u) x tile_v, MMA N = 8*Ny
+// tap-sharing: tiles are 14 interior (16 with halo) x tile_v, MMA N = 16*Ny; cost counts MMA columns
+static OperandPlan plan_operand(int H, int W, bool is_key, bool shared, int force_orient = -1, double* cost_out = nullptr) {
   OperandPlan best{};
   double best_cost = 1e300;
+  const int tile_u = shared ? kSTileU : kTileU, cols_u = shared ? kSBoxU : kTileU;
+  const int qv = shared ? kSQTileV : kQTileV, max_ny = shared ? kSMaxNy : kMaxNy;
   for (int orient = 0; orient < 2; ++orient) {
+    if (force_orient >= 0 && orient != force_orient) continue;
     const int U = orient == 0 ? W : H, V = orient == 0 ? H : W;
-    const int ny_lo = is_key ? 2 : kQTileV, ny_hi = is_key ? kMaxNy : kQTileV;
-    for (int ny = ny_hi; ny >= ny_lo; ny -= 2) {
+    const int ny_lo = is_key ? (shared ? 1 : 2) : qv, ny_hi = is_key ? max_ny : qv;
+    for (int ny = ny_hi; ny >= ny_lo; ny -= (shared ? 1 : 2)) {
       OperandPlan o{};
-      o.orient = orient; o.U = U; o.V = V; o.tile_v = ny;
-      o.tu = ceil_div(U, kTileU); o.tv = ceil_div(V, ny);
-      o.Upad = o.tu * kTileU + 2; o.Vpad = o.tv * ny + 2;
-      double cost = (double)o.tu * kTileU * o.tv * ny;
+      o.orient = orient; o.U = U; o.V = V; o.tile_u = tile_u; o.tile_v = ny;
+      o.tu = ceil_div(U, tile_u); o.tv = ceil_div(V, ny);
+      o.Upad = o.tu * tile_u + 2; o.Vpad = o.tv * ny + 2;
+      double cost = (double)o.tu * cols_u * o.tv * ny;
       if (is_key) {
         // narrower MMA N re-reads the 4 KB query operand more often per flop: shared-memory
         // bytes per cycle = 8192/N + 64; penalise N below ~192
-        const double n_cols = 8.0 * ny, bpc = 8192.0 / n_cols + 64.0;
+        const double n_cols = (double)cols_u * ny, bpc = 8192.0 / n_cols + 64.0;
         if (bpc > 104.0) cost *= bpc / 104.0;
       }
       if (cost < best_cost - 1e-9) { best_cost = cost; best = o; }
     }
   }
+  if (cost_out) *cost_out = best_cost;
   return best;
 }
 
@@ -55,9 +61,24 @@ static long long cta_of_pair(long long p, long long P, int G) { return ((p + 1) 
 
 int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   Plan p{};
+  const bool shared = s.search == SPEI_SEARCH_TCS;
+  p.mode = shared ? SPEI_SEARCH_TCS : SPEI_SEARCH_TC;
+  p.nlist = shared ? 2 : 1;
   p.n = s.n; p.rf = s.rf; p.H = s.h; p.W = s.w; p.Hr = s.hr; p.Wr = s.wr;
-  p.q = plan_operand(s.h, s.w, false);
-  p.k = plan_operand(s.hr, s.wr, true);
+  if (!shared) {
+    // the MMA applies all nine taps with per-operand address offsets: each operand picks its own orientation
+    p.q = plan_operand(s.h, s.w, false, false);
+    p.k = plan_operand(s.hr, s.wr, true, false);
+  } else {
+    // the u taps are summed in the epilogue for both operands at once: u must be the same image axis for both
+    double best = 1e300;
+    for (int orient = 0; orient < 2; ++orient) {
+      double cq = 0, ck = 0;
+      const OperandPlan oq = plan_operand(s.h, s.w, false, true, orient, &cq);
+      const OperandPlan ok = plan_operand(s.hr, s.wr, true, true, orient, &ck);
+      if (cq * ck < best - 1e-9) { best = cq * ck; p.q = oq; p.k = ok; }
+    }
+  }
   p.QT = p.q.tiles();
   p.KT = p.rf * p.k.tiles();
   p.P = (long long)p.n * p.QT * p.KT;
@@ -79,9 +100,10 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.off_kss = take(nk * Lk1 * 4);
   p.off_rq = take(nq * L * 4);
   p.off_rk = take(nk * Lk1 * 4);
-  p.off_rkpad = take(nk * (size_t)(p.k.tv * p.k.tile_v) * (p.k.tu * kTileU) * 4);
-  p.off_cval = take(nq * L * p.maxseg * kTopK * 4);
-  p.off_cidx = take(nq * L * p.maxseg * kTopK * 4);
+  // dense: [tv*Ny][tu*8] tile-padded; tap-sharing: [tv*Ny][tu*14 + 2] with a 1-position border
+  p.off_rkpad = take(nk * (size_t)(p.k.tv * p.k.tile_v) * (shared ? p.k.Upad : p.k.tu * kTileU) * 4);
+  p.off_cval = take(nq * L * p.maxseg * p.nlist * kTopK * 4);
+  p.off_cidx = take(nq * L * p.maxseg * p.nlist * kTopK * 4);
   p.off_flag = take(nq * L * 4);
   p.off_packed = take(nq * L * 8);
   p.off_arg32 = take(nq * L * 4);
@@ -122,7 +144,9 @@ static int check_shape(const SpeiShape* s) {
     set_error("index space exceeds int32"); return SPEI_ERR_ARG;
   }
   if (s->fold_mode < 0 || s->fold_mode > 3) { set_error("bad fold_mode %d", s->fold_mode); return SPEI_ERR_ARG; }
-  if (s->search != SPEI_SEARCH_TC && s->search != SPEI_SEARCH_EXACT) { set_error("bad search %d", s->search); return SPEI_ERR_ARG; }
+  if (s->search != SPEI_SEARCH_TC && s->search != SPEI_SEARCH_EXACT && s->search != SPEI_SEARCH_TCS) {
+    set_error("bad search %d", s->search); return SPEI_ERR_ARG;
+  }
   return SPEI_OK;
 }
 
@@ -184,7 +208,9 @@ int spei_relevance_candidates(const SpeiShape* shape, void* workspace, size_t wo
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
   if (rc) return rc;
-  return launch_relevance_tc(p, shape->eps > 0.f ? shape->eps : 2e-3f, (char*)workspace, (cudaStream_t)stream);
+  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  return p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, (char*)workspace, (cudaStream_t)stream)
+                                   : launch_relevance_tc(p, eps, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_rescore(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, void* workspace,
@@ -209,7 +235,7 @@ int spei_relevance_argmax(const SpeiShape* shape, float* S, int32_t* arg32, int6
   if (stats) SPEI_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
   if (shape->search == SPEI_SEARCH_EXACT) return launch_exact_all(p, S, arg32, arg64, ws, st);
   const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
-  rc = launch_relevance_tc(p, eps, ws, st);
+  rc = p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, ws, st) : launch_relevance_tc(p, eps, ws, st);
   if (rc) return rc;
   return launch_rescore(p, eps, S, arg32, arg64, stats, ws, st);
 }
@@ -220,7 +246,9 @@ int spei_debug_relevance_tile(const SpeiShape* shape, float* acc_out, void* work
   if (rc) return rc;
   if ((rc = check_ptr(acc_out, "acc_out", 16))) return rc;
   set_debug_acc(acc_out);
-  return launch_relevance_tc(p, shape->eps > 0.f ? shape->eps : 2e-3f, (char*)workspace, (cudaStream_t)stream);
+  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  return p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, (char*)workspace, (cudaStream_t)stream)
+                                   : launch_relevance_tc(p, eps, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_debug_error_flag(const SpeiShape* shape, void* workspace, size_t workspace_bytes, void* stream, int32_t* host_out) {

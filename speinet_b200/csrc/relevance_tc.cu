@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include "spei_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace spei {
 
@@ -62,99 +63,9 @@ struct TcParams {
   int* error_flag;   // set on a barrier timeout
 };
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as an error code, not as a hung GPU.  On a ~2 s timeout the
-// waiter records which barrier starved in *error_flag; from then on every wait in the grid returns
-// immediately, so the kernel drains (with garbage results) and the host can read the code back.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0) {
-      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
-      if (clock64() - t0 > 4000000000ll) {
-        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
-        return;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no swizzle: bits 0-13 start>>4, 16-29 LBO>>4, 32-45 SBO>>4, 46-47 version=1 (sm_100), 61-63 layout 0
+// K-major, no swizzle, SBO = one halo-tile row
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(kRowBytes >> 4) << 32) |
-         (1ull << 46);
-}
-
-struct PairIdx { int item, qt, kt; };
-__device__ __forceinline__ PairIdx next_pair(PairIdx r, int QT, int KT) {
-  if (++r.kt == KT) { r.kt = 0; if (++r.qt == QT) { r.qt = 0; ++r.item; } }
-  return r;
-}
-__device__ __forceinline__ PairIdx decode_pair(long long p, int QT, int KT) {
-  PairIdx r;
-  const long long per_item = (long long)QT * KT;
-  r.item = (int)(p / per_item);
-  const int rem = (int)(p - (long long)r.item * per_item);
-  r.qt = rem / KT;
-  r.kt = rem - r.qt * KT;
-  return r;
+  return umma_desc_kmajor(saddr, lbo_bytes, kRowBytes);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -398,11 +309,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int get_encode_fn(EncodeTiledFn* out) {
+int get_encode_fn(EncodeTiledFn* out) {
   static EncodeTiledFn cached = nullptr;
   if (!cached) {
     void* fn = nullptr;
@@ -469,5 +376,6 @@ int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st) {
 }
 
 void set_debug_acc(float* ptr) { tl_debug_acc = ptr; }
+float* take_debug_acc() { float* r = tl_debug_acc; tl_debug_acc = nullptr; return r; }
 
 }  // namespace spei

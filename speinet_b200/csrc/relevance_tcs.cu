@@ -1,0 +1,348 @@
+// Kernel (b), tap-sharing variant: relevance bmm + row-wise max / argmax
+// (/root/reference/model/SearchTransfer.py:33-34) with the 3x3 patch sum split between the tensor
+// cores and the epilogue.
+//
+//   R[j, i] = rk[j] * rq[i] * sum_{tu in -1..1} D[j + tu*e_u, i + tu*e_u]
+//   D[j, i] = sum_{tv in -1..1} sum_c K[c, j + tv*e_v] * Q[c, i + tv*e_v]          (e_u, e_v: unit steps in u, v)
+//
+// D is a dense contraction with K = 3 taps x 128 channels = 384 and runs on tcgen05 exactly like the
+// dense kernel (relevance_tc.cu) but with a third of the MMAs.  The missing sum over the u taps adds
+// three *neighbouring* accumulator entries: the product for (query i, key j, tap tu) is the tv-partial
+// of (query i + tu, key j + tu), which the dense kernel recomputes for every one of them.  Tiles are
+// 16 positions wide along u, MMA row m = v*16 + u, MMA column c = v'*16 + u', so the neighbours are
+// (m-1, c-1) and (m+1, c+1): one TMEM lane up / down -- a warp shuffle, never leaving the 16-lane
+// half-warp -- and one accumulator column left / right, which the thread already holds.  The outer
+// positions u = 0 and u = 15 of a tile are halo (consumed, not produced), so tiles advance by 14: 112
+// of 128 rows and 14 of 16 columns per key row are productive, and the tensor-core work drops
+// 3 * (14/16)^2 = 2.3x against the dense kernel for identical bf16 scores (same products, fp32 sums).
+//
+// Operand layout: the same channel-group-planar bf16 images as the dense kernel ([16][Vpad][Upad][8],
+// zero border).  A tile row is exactly 16 positions x 16 B = 256 B, so the canonical no-swizzle
+// K-major core matrices (8 rows x 16 B) of MMA rows 8g..8g+7 sit at g*128 B: SBO = 128 B, LBO = one
+// channel-group plane of the tile, tap tv = start address + tv*256 B.  One TMA box per operand tile.
+//
+// Per CTA (persistent, one per SM, 12 warps):
+//   warp 0    TMA producer (query tile 40 KB resident per query tile, ring of key stages)
+//   warp 1    MMA issuer: per key tile 8 K16-steps x 3 taps = 24 tcgen05.mma (M=128, N=16*Ny)
+//   warp 2    TMEM allocator (2 x 256 columns, double-buffered accumulators)
+//   warps 4-11 epilogue, two groups of four: group h handles key rows [h*ceil(Ny/2), ...) of every tile and
+//             keeps its own top-k list per query (the rescoring merges lists)
+#include <cuda.h>
+
+#include "spei_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace spei {
+
+constexpr int kSThreads = 384;
+constexpr uint32_t kSRowBytes = kSBoxU * 16;                                  // 256 B
+constexpr uint32_t kSSBO = 128;                                               // 8 positions x 16 B
+constexpr uint32_t kSQRows = kSQTileV + 2;                                    // 10
+constexpr uint32_t kSQLBO = kSQRows * kSRowBytes;                             // 2560
+constexpr uint32_t kSQTileBytes = kCG * kSQLBO;                               // 40960
+constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       // 18432
+constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
+constexpr uint32_t kSNumBars = 2 * kStages + 6;
+constexpr uint32_t kSRkOffset = kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
+constexpr uint32_t kSSmemBytes = kSRkOffset + 8 * 128 * 4;
+static_assert(kSRkOffset % 16 == 0, "key-norm staging must be float4 aligned");
+constexpr uint32_t kSTmemCols = 512;
+constexpr uint32_t kSAccCols = 256;
+
+struct TcsParams {
+  int n, rf, QT, KT, G, maxseg;
+  long long P;
+  int q_tu, q_orient, Uq, Vq, W, L;
+  int k_tu, k_tiles_img, k_orient, Ny, Wr, lk1, UkP, VkT;
+  uint32_t idesc, stage_bytes, k_lbo;
+  float win;
+  const float* rq;
+  const float* rkpad;  // [img][VkT][UkP], u border included, NaN outside the image
+  float* cval;
+  int32_t* cidx;
+  float* debug_acc;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kSThreads, 1)
+relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const TcsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + kSQTileBytes;
+  const uint32_t bars = sK + kStages * kSStageBytesMax;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages;
+  const uint32_t bar_qfull = bars + 16 * kStages, bar_qfree = bar_qfull + 8;
+  const uint32_t bar_tfull = bar_qfull + 16, bar_tempty = bar_qfull + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const long long pb = (long long)b * p.P / p.G, pe = (long long)(b + 1) * p.P / p.G;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_qfull, 1); mbar_init(bar_qfree, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmq) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmk) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kSTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int qloaded = 0;
+      PairIdx ix = decode_pair(pb, p.QT, p.KT);
+      for (long long pp = pb; pp < pe; ++pp, ix = next_pair(ix, p.QT, p.KT)) {
+        if (pp == pb || ix.kt == 0) {
+          if (qloaded > 0) mbar_wait(bar_qfree, (uint32_t)((qloaded - 1) & 1), p.error_flag);
+          const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
+          mbar_arrive_expect_tx(bar_qfull, kSQTileBytes);
+          // staged coordinates carry a 1-position border: interior position (u, v) lives at (u+1, v+1); the box
+          // starts one position before the tile's first interior position in both directions
+          tma_load_4d(sQ, &tmq, bar_qfull, qtu * kSTileU * 8, qtv * kSQTileV, 0, ix.item);
+          ++qloaded;
+        }
+        const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
+        const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
+        for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes);
+          tma_load_4d(sK + stage * kSStageBytesMax, &tmk, bar_full + 8 * stage, ktu * kSTileU * 8, ktv * p.Ny, (int)(s4 * kCGS),
+                      ix.item * p.rf + f);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int qused = 0;
+      uint32_t tile_i = 0;
+      PairIdx ix = decode_pair(pb, p.QT, p.KT);
+      for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
+        if (pp == pb || ix.kt == 0) {
+          mbar_wait(bar_qfull, (uint32_t)(qused & 1), p.error_flag);
+          ++qused;
+        }
+        const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
+        mbar_wait(bar_tempty + 8 * acc, (use & 1u) ^ 1u, p.error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kSAccCols;
+        for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
+          mbar_wait(bar_full + 8 * stage, phase, p.error_flag);
+          tc_fence_after();
+          const uint32_t kbase = sK + stage * kSStageBytesMax;
+#pragma unroll
+          for (uint32_t cgp = 0; cgp < kCGS / 2; ++cgp) {
+            const uint32_t qa = sQ + (s4 * kCGS + cgp * 2) * kSQLBO;
+            const uint32_t ka = kbase + (cgp * 2) * p.k_lbo;
+#pragma unroll
+            for (uint32_t tap = 0; tap < 3; ++tap) {
+              const uint64_t adesc = umma_desc_kmajor(qa + tap * kSRowBytes, kSQLBO, kSSBO);
+              const uint64_t bdesc = umma_desc_kmajor(ka + tap * kSRowBytes, p.k_lbo, kSSBO);
+              tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (s4 | cgp | tap) != 0u);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (ix.kt == p.KT - 1 && pp + 1 < pe) tc_commit(bar_qfree);
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int ew = (warp - 4) & 3;        // TMEM lane quarter this warp may read (= warp % 4)
+    const int half = (warp - 4) >> 2;     // which half of a tile's key rows
+    const int m = ew * 32 + lane;         // MMA row: query (qu = m % 16, qv = m / 16) of the tile
+    const int qu = m & 15, qv = m >> 4;
+    const int r_lo = half == 0 ? 0 : (p.Ny + 1) / 2, r_hi = half == 0 ? (p.Ny + 1) / 2 : p.Ny;
+    float tv[kTopK];
+    int ti[kTopK];
+    uint32_t tile_i = 0;
+    long long qlin = -1;
+    float winq = 0.f;
+    float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * 128;  // this warp's key norms: [rows][16]
+    // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=8 rows][16] reciprocal norms
+    auto rk_prefetch = [&](const PairIdx ix, float2 (&pre)[2]) {
+      const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
+      const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
+      const float* base = p.rkpad + ((size_t)(ix.item * p.rf + f) * p.VkT + ktv * p.Ny + r_lo) * p.UkP + ktu * kSTileU;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e2 = lane + 32 * j, row = e2 >> 3;
+        pre[j] = (r_lo + row) < r_hi ? __ldg(reinterpret_cast<const float2*>(base + (size_t)row * p.UkP) + (e2 & 7))
+                                     : make_float2(0.f, 0.f);
+      }
+    };
+    float2 pre[2];
+    PairIdx ix = decode_pair(pb, p.QT, p.KT);
+    if (pb < pe) rk_prefetch(ix, pre);
+    for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
+      if (pp == pb || ix.kt == 0) {
+#pragma unroll
+        for (int s = 0; s < kTopK; ++s) { tv[s] = -INFINITY; ti[s] = -1; }
+        const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
+        const int u = qtu * kSTileU + qu - 1, v = qtv * kSQTileV + qv;
+        qlin = (qu >= 1 && qu <= kSTileU && u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
+        winq = qlin >= 0 ? p.win / __ldg(p.rq + qlin) : 0.f;
+      }
+      const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
+      const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
+      const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
+      const int ku0 = ktu * kSTileU - 1, kv0 = ktv * p.Ny;
+      __syncwarp();
+      reinterpret_cast<float2*>(rk_s)[lane] = pre[0];
+      reinterpret_cast<float2*>(rk_s)[lane + 32] = pre[1];
+      __syncwarp();
+      if (pp + 1 < pe) rk_prefetch(next_pair(ix, p.QT, p.KT), pre);
+      mbar_wait(bar_tfull + 8 * acc, use & 1u, p.error_flag);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kSAccCols + ((uint32_t)(ew * 32) << 16);
+
+      uint32_t a[16];
+      if (r_lo < r_hi) tc_ld16(taddr + r_lo * 16, a);
+      for (int r = r_lo; r < r_hi; ++r) {
+        tc_wait_ld();
+        float d[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(a[i]);
+        if (p.debug_acc && pp == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) p.debug_acc[(size_t)m * kSAccCols + r * 16 + i] = d[i];
+        }
+        if (r + 1 < r_hi) tc_ld16(taddr + (r + 1) * 16, a);  // refill a[] asynchronously while d[] is processed
+        // sum of the three u taps: (m-1, c-1) + (m, c) + (m+1, c+1), scaled by the key's reciprocal norm
+        float v[16];
+        v[0] = -INFINITY; v[15] = -INFINITY;  // halo columns: keys of the neighbouring tiles
+        float rkr[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 t4 = reinterpret_cast<const float4*>(rk_s + (r - r_lo) * 16)[i4];  // broadcast read
+          rkr[4 * i4] = t4.x; rkr[4 * i4 + 1] = t4.y; rkr[4 * i4 + 2] = t4.z; rkr[4 * i4 + 3] = t4.w;
+        }
+#pragma unroll
+        for (int i = 1; i < 15; ++i) {
+          const float up = __shfl_up_sync(0xffffffffu, d[i - 1], 1);
+          const float dn = __shfl_down_sync(0xffffffffu, d[i + 1], 1);
+          v[i] = ((up + dn) + d[i]) * rkr[i];  // NaN for keys outside the image
+        }
+        float mx = fmaxf(fmaxf(fmaxf(v[1], v[2]), fmaxf(v[3], v[4])), fmaxf(fmaxf(v[5], v[6]), fmaxf(v[7], v[8])));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(v[9], v[10]), fmaxf(v[11], v[12])), fmaxf(v[13], v[14])));
+        const float thr = fmaxf(tv[kTopK - 1], tv[0] - winq);
+        if (qlin >= 0 && mx > thr) {
+          unsigned msk = 0;
+#pragma unroll
+          for (int i = 1; i < 15; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
+          while (msk) {
+            const int i = __ffs(msk) - 1;
+            msk &= msk - 1;
+            float s8[8], s4[4], s2[2];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s8[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = (i & 2) ? s8[2 * j + 1] : s8[2 * j];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) s2[j] = (i & 4) ? s4[2 * j + 1] : s4[2 * j];
+            float x = (i & 8) ? s2[1] : s2[0];
+            if (x > fmaxf(tv[kTopK - 1], tv[0] - winq)) {
+              int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku0 + i, kv0 + r, p.Wr);
+#pragma unroll
+              for (int s = 0; s < kTopK; ++s) {
+                if (x > tv[s]) {
+                  const float tf = tv[s]; tv[s] = x; x = tf;
+                  const int tj = ti[s]; ti[s] = xi; xi = tj;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (pp + 1 == pe || ix.kt == p.KT - 1) {
+        if (qlin >= 0) {
+          const long long p0 = ((long long)ix.item * p.QT + ix.qt) * p.KT;
+          const int slot = (b - (int)(((p0 + 1) * (long long)p.G - 1) / p.P)) * 2 + half;
+          float4* dv = reinterpret_cast<float4*>(p.cval + ((size_t)qlin * p.maxseg * 2 + slot) * kTopK);
+          int4* di = reinterpret_cast<int4*>(p.cidx + ((size_t)qlin * p.maxseg * 2 + slot) * kTopK);
+#pragma unroll
+          for (int s4 = 0; s4 < kTopK / 4; ++s4) {
+            dv[s4] = make_float4(tv[4 * s4], tv[4 * s4 + 1], tv[4 * s4 + 2], tv[4 * s4 + 3]);
+            di[s4] = make_int4(ti[4 * s4], ti[4 * s4 + 1], ti[4 * s4 + 2], ti[4 * s4 + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// 4-D map over a staged operand [img][16][Vpad][Upad*8] bf16; box = [1][groups][rows][16 positions x 8 channels]
+static int make_map_s(EncodeTiledFn enc, CUtensorMap* tm, void* base, int nimg, const OperandPlan& o, int box_rows, int box_groups) {
+  const cuuint64_t dims[4] = {(cuuint64_t)o.Upad * 8, (cuuint64_t)o.Vpad, (cuuint64_t)kCG, (cuuint64_t)nimg};
+  const cuuint64_t strides[3] = {(cuuint64_t)o.Upad * 16, (cuuint64_t)o.Vpad * o.Upad * 16, (cuuint64_t)kCG * o.Vpad * o.Upad * 16};
+  const cuuint32_t box[4] = {kSBoxU * 8, (cuuint32_t)box_rows, (cuuint32_t)box_groups, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
+  return SPEI_OK;
+}
+
+int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  CUtensorMap tmq, tmk;
+  if ((rc = make_map_s(enc, &tmq, ws + p.off_qbf, p.n, p.q, kSQTileV + 2, kCG))) return rc;
+  if ((rc = make_map_s(enc, &tmk, ws + p.off_kbf, p.n * p.rf, p.k, p.k.tile_v + 2, kCGS))) return rc;
+
+  TcsParams t{};
+  t.n = p.n; t.rf = p.rf; t.QT = p.QT; t.KT = p.KT; t.G = p.G; t.maxseg = p.maxseg; t.P = p.P;
+  t.q_tu = p.q.tu; t.q_orient = p.q.orient; t.Uq = p.q.U; t.Vq = p.q.V; t.W = p.W; t.L = p.H * p.W;
+  t.k_tu = p.k.tu; t.k_tiles_img = p.k.tiles(); t.k_orient = p.k.orient; t.Ny = p.k.tile_v; t.Wr = p.Wr; t.lk1 = p.Hr * p.Wr;
+  t.UkP = p.k.Upad; t.VkT = p.k.tv * p.k.tile_v;
+  const uint32_t ncols = (uint32_t)(kSBoxU * p.k.tile_v);
+  // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bits 17-22, M>>4 at bits 24-28
+  t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
+  t.k_lbo = (uint32_t)(p.k.tile_v + 2) * kSRowBytes;
+  t.stage_bytes = kCGS * t.k_lbo;
+  t.win = eps * 1.02f;
+  t.rq = (const float*)(ws + p.off_rq);
+  t.rkpad = (const float*)(ws + p.off_rkpad);
+  t.cval = (float*)(ws + p.off_cval);
+  t.cidx = (int32_t*)(ws + p.off_cidx);
+  t.debug_acc = take_debug_acc();
+  t.error_flag = (int*)(ws + p.off_errflag);
+  SPEI_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int), st));
+  SPEI_CUDA(cudaFuncSetAttribute(relevance_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes));
+  SPEI_CUDA(cudaFuncSetAttribute(relevance_tcs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
+  relevance_tcs_kernel<<<p.G, kSThreads, kSSmemBytes, st>>>(tmq, tmk, t);
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
+}
+
+}  // namespace spei

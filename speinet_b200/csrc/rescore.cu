@@ -32,7 +32,7 @@ __device__ __forceinline__ unsigned long long pack_score(float s, int j) {
 
 struct RescoreParams {
   int n, rf, H, W, Hr, Wr;
-  int q_orient, q_tu;       // query tile grid (to find a query's tile -> its segment count)
+  int q_orient, q_tu, q_tile_u, q_tile_v, nlist;  // query tile grid (to find a query's tile -> its segment count)
   int QT, KT, G, maxseg;
   long long P;
   float eps;
@@ -79,12 +79,13 @@ rescore_kernel(const RescoreParams p) {
 
   // which query tile is this, and into how many key segments was it split?
   const int u = p.q_orient == 0 ? x : y, v = p.q_orient == 0 ? y : x;
-  const int qt = (v / kQTileV) * p.q_tu + (u / kTileU);
+  const int qt = (v / p.q_tile_v) * p.q_tu + (u / p.q_tile_u);
   const long long p0 = ((long long)n * p.QT + qt) * p.KT;
   const int nseg = (int)(cta_of_pair_d(p0 + p.KT - 1, p.P, p.G) - cta_of_pair_d(p0, p.P, p.G)) + 1;
-  const int ncand = nseg * kTopK;
-  const float* cv = p.cval + (size_t)wq * p.maxseg * kTopK;
-  const int32_t* ci = p.cidx + (size_t)wq * p.maxseg * kTopK;
+  const int nlists = nseg * p.nlist;  // lists of a query are contiguous: [segment][list][kTopK]
+  const int ncand = nlists * kTopK;
+  const float* cv = p.cval + (size_t)wq * p.maxseg * p.nlist * kTopK;
+  const int32_t* ci = p.cidx + (size_t)wq * p.maxseg * p.nlist * kTopK;
 
   // independent loads first: patch energy (zero test), query norm, first 32 candidates
   float s = 0.f;
@@ -123,7 +124,7 @@ rescore_kernel(const RescoreParams p) {
 
   // saturation: the last (smallest) entry of some segment is still inside the window
   bool sat = false;
-  for (int sg = lane; sg < nseg; sg += 32) {
+  for (int sg = lane; sg < nlists; sg += 32) {
     const int e = sg * kTopK + (kTopK - 1);
     if (__ldg(ci + e) >= 0 && __ldg(cv + e) * rq >= thr) sat = true;
   }
@@ -443,7 +444,7 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   if (rc) return rc;
   RescoreParams r{};
   r.n = p.n; r.rf = p.rf; r.H = p.H; r.W = p.W; r.Hr = p.Hr; r.Wr = p.Wr;
-  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.QT = p.QT; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
+  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.QT = p.QT; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
   r.eps = eps;
   r.q32 = (const float*)(ws + p.off_q32); r.k32 = (const float*)(ws + p.off_k32);
   r.rq = (const float*)(ws + p.off_rq); r.rk = (const float*)(ws + p.off_rk); r.qss = (const float*)(ws + p.off_qss);

@@ -20,6 +20,12 @@ constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA 
 #define SPEI_TOPK 16
 #endif
 constexpr int kTopK = SPEI_TOPK;  // bf16-pass candidates kept per query per key segment (multiple of 4)
+// tap-sharing search (relevance_tcs.cu): tiles are 16 wide along u (14 interior + a 1-pixel halo each side,
+// the u taps are summed in the epilogue), queries 8 rows, keys up to 16 rows
+constexpr int kSTileU = 14;       // interior tile extent along u
+constexpr int kSBoxU = 16;        // shared-memory tile extent along u = one 256-byte row
+constexpr int kSQTileV = 8;       // query tile: 16 x 8 positions = 128 MMA rows (112 of them interior)
+constexpr int kSMaxNy = 16;       // key tile: 16 x Ny positions = up to 256 MMA columns
 constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
 constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight)
 
@@ -28,13 +34,16 @@ constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight
 struct OperandPlan {
   int orient;
   int U, V;        // valid extent
-  int tile_v;      // tile height along v (16 for queries, Ny for keys)
+  int tile_u;      // tile stride along u (8 dense; 14 tap-sharing)
+  int tile_v;      // tile height along v (16 / 8 for queries, Ny for keys)
   int tu, tv;      // tiles along u / v
   int Upad, Vpad;  // staged bf16 plane = [Vpad][Upad] pixels, 1-pixel zero border included
   __host__ __device__ int tiles() const { return tu * tv; }
 };
 
 struct Plan {
+  int mode;        // SPEI_SEARCH_TC (dense 9-tap MMA) or SPEI_SEARCH_TCS (tap-sharing); decides the operand tiling
+  int nlist;       // candidate lists per (query, key segment): 1 dense, 2 tap-sharing (two epilogue warp groups)
   int n, rf;
   int H, W, Hr, Wr;
   OperandPlan q, k;
@@ -63,6 +72,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // ---- stage launchers (defined in the .cu files) -----------------------------------------------
 int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st);
 int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st);
+int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st);
 void set_debug_acc(float* ptr);
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st);

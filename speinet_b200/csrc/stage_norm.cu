@@ -8,7 +8,8 @@
 //         halo tile in shared memory.
 //   * x32 [img][H][W][128] fp32 (NHWC)   -- read by the exact fp32 rescoring with 512-byte rows.
 //   * r   [img][H*W] fp32                -- 1 / max(||3x3x128 patch||_2, 1e-12)  (F.normalize, :30-31)
-//   * rkpad (keys) [img][tv*Ny][tu*8]    -- r in tile-padded (u,v) order, NaN for padded positions so
+//   * rkpad (keys) [img][tv*Ny][tu*8] (dense) or [img][tv*Ny][Upad] (tap-sharing, u border included)
+//         -- r in tile-padded (u,v) order, NaN for padded positions so
 //         that a padded key can never win a comparison in the relevance epilogue.
 #include "spei_common.cuh"
 
@@ -91,16 +92,16 @@ patch_norm_kernel(const float* __restrict__ ss, int nimg, int H, int W, float* _
 }
 
 __global__ void __launch_bounds__(256)
-key_norm_padded_kernel(const float* __restrict__ ss, int nimg, int H, int W, int orient, int UT, int VT,
+key_norm_padded_kernel(const float* __restrict__ ss, int nimg, int H, int W, int orient, int UT, int VT, int border,
                        float* __restrict__ rkpad) {
   const size_t per = (size_t)UT * VT;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per * nimg) return;
   const int img = (int)(i / per), rem = (int)(i % per);
-  const int v = rem / UT, u = rem % UT;
+  const int v = rem / UT, u = rem % UT - border;
   const int x = orient == 0 ? u : v, y = orient == 0 ? v : u;
   float out = __int_as_float(0x7fc00000);  // NaN: padded keys never compare greater
-  if (x < W && y < H) out = patch_rnorm(ss + (size_t)img * H * W, H, W, y, x);
+  if (u >= 0 && x < W && y < H) out = patch_rnorm(ss + (size_t)img * H * W, H, W, y, x);
   rkpad[i] = out;
 }
 
@@ -114,9 +115,11 @@ static int stage_operand(const float* x, int nimg, int H, int W, const OperandPl
   patch_norm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ss, nimg, H, W, r);
   SPEI_CUDA(cudaGetLastError());
   if (rkpad) {
-    const int UT = o.tu * kTileU, VT = o.tv * o.tile_v;
+    // dense tiling: [tv*Ny][tu*8]; tap-sharing tiling: [tv*Ny][Upad] with the staged image's 1-position u border
+    const bool shared = o.tile_u == kSTileU;
+    const int UT = shared ? o.Upad : o.tu * kTileU, VT = o.tv * o.tile_v;
     const size_t totp = (size_t)nimg * UT * VT;
-    key_norm_padded_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(ss, nimg, H, W, o.orient, UT, VT, rkpad);
+    key_norm_padded_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(ss, nimg, H, W, o.orient, UT, VT, shared ? 1 : 0, rkpad);
     SPEI_CUDA(cudaGetLastError());
   }
   return SPEI_OK;

@@ -24,7 +24,7 @@ from . import _lib
 
 TensorOrList = Union[torch.Tensor, Sequence[torch.Tensor]]
 _FOLD = {"cuda": _lib.FOLD_CUDA, "cpu": _lib.FOLD_CPU}
-_SEARCH = {"tc": _lib.SEARCH_TC, "exact": _lib.SEARCH_EXACT}
+_SEARCH = {"tc": _lib.SEARCH_TC, "exact": _lib.SEARCH_EXACT, "tcs": _lib.SEARCH_TCS}
 
 
 def _ptr(t):

@@ -92,6 +92,10 @@ def search_transfer_torch_with_index(g, lvl):
 def compare_search(name, q, k_list, S, arg32, ref_S, ref_arg):
     agree, n_eq, n_tie = oracle.near_tie_agreement(q, k_list, arg32, ref_arg)
     rel = np.abs(S - ref_S) / np.maximum(np.abs(ref_S), 1e-6)
+    bad = np.argwhere(~agree)
+    if bad.size:  # first few offenders: (item, query, got index, want index, got S, want S)
+        print("mismatches", [(int(a), int(b), int(arg32[a, b]), int(ref_arg[a, b]), float(S[a, b]), float(ref_S[a, b])) for a, b in bad[:24]],
+              flush=True)
     return {"case": name, "queries": int(agree.size), "equal": n_eq, "near_tie": n_tie, "mismatch": int((~agree).sum()),
             "S_max_rel_err": float(rel.max()), "S_max_abs_err": float(np.abs(S - ref_S).max())}
 
@@ -122,14 +126,14 @@ def stage_search(search, label):
     REC["cases"] = cases
 
 
-def stage_tile():
+def stage_tile(search=_lib.SEARCH_TC):
     out = []
     rng = np.random.default_rng(11)
     for (h, w, hr, wr) in ((16, 8, 32, 8), (20, 24, 20, 24), (64, 64, 64, 64), (37, 50, 29, 44)):
         q = (rng.standard_normal((1, 128, h, w))).astype(np.float32)
         k = (rng.standard_normal((1, 128, hr, wr))).astype(np.float32)
-        acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous())
-        want = U.expected_debug_tile(q, k, info)
+        acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous(), search=search)
+        want = (U.expected_debug_tile_tcs if search == _lib.SEARCH_TCS else U.expected_debug_tile)(q, k, info)
         ncol = want.shape[1]
         got = acc[:, :ncol].astype(np.float64)
         err = np.abs(got - want)
@@ -174,7 +178,7 @@ def timed(fn, iters=5, warm=2):
     return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))[iters // 2]
 
 
-def stage_robust():
+def stage_robust(search=_lib.SEARCH_TC):
     """Image-like (smooth, self-similar) features at full 720p size: how many queries saturate their
     candidate list, what the fallback costs, and whether the result still equals the exhaustive fp32 search."""
     import torch.nn.functional as F
@@ -193,17 +197,17 @@ def stage_robust():
             k = torch.randn(1, 128, h, w, device="cuda") * 0.04
         k5 = k.unsqueeze(1).contiguous()
         t0 = time.time()
-        S, a, st, fl = U.run_search(q, k5)
+        S, a, st, fl = U.run_search(q, k5, search=search)
         t_tc = time.time() - t0
-        ms = timed(lambda: U.run_search(q, k5), iters=3, warm=1)
+        ms = timed(lambda: U.run_search(q, k5, search=search), iters=3, warm=1)
         S2, a2, _, _ = U.run_search(q, k5, search=_lib.SEARCH_EXACT)
         diff = (a != a2)
         r = {"case": name, "stats": st.cpu().tolist(), "error_flag": fl, "ms_search_incl_host_overhead": ms,
              "index_mismatch_vs_exhaustive": int(diff.sum()), "S_max_abs_diff": float((S - S2).abs().max()),
              "S_mean": float(S.mean()), "first_call_s": t_tc}
         for eps in (1e-3, 4e-3, 8e-3):  # 8e-3 = rigorous two-sided worst-case bound 2^-7 of bf16 operand rounding
-            Se, ae, ste, _ = U.run_search(q, k5, eps=eps)
-            mse = timed(lambda: U.run_search(q, k5, eps=eps), iters=3, warm=1)
+            Se, ae, ste, _ = U.run_search(q, k5, eps=eps, search=search)
+            mse = timed(lambda: U.run_search(q, k5, eps=eps, search=search), iters=3, warm=1)
             r[f"eps_{eps:g}"] = {"stats": ste.cpu().tolist(), "ms": mse, "mismatch_vs_exhaustive": int((ae != a2).sum())}
         out.append(r)
         print("robust", r, flush=True)
@@ -327,6 +331,8 @@ def main():
     t0 = time.time()
     fn = {"env": stage_env, "fold": stage_fold, "exact": lambda: stage_search(_lib.SEARCH_EXACT, "exact"),
           "tc": lambda: stage_search(_lib.SEARCH_TC, "tc"), "tile": stage_tile, "fuse": stage_fuse,
+          "tcs": lambda: stage_search(_lib.SEARCH_TCS, "tcs"), "tile_tcs": lambda: stage_tile(_lib.SEARCH_TCS),
+          "robust_tcs": lambda: stage_robust(_lib.SEARCH_TCS),
           "time720": stage_time720, "robust": stage_robust, "configs": stage_configs, "gather": stage_gather}[a.stage]
     try:
         fn()
