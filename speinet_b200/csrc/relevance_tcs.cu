@@ -9,24 +9,26 @@
 // dense kernel (relevance_tc.cu) but with a third of the MMAs.  The missing sum over the u taps adds
 // three *neighbouring* accumulator entries: the product for (query i, key j, tap tu) is the tv-partial
 // of (query i + tu, key j + tu), which the dense kernel recomputes for every one of them.  Tiles are
-// 16 positions wide along u, MMA row m = v*16 + u, MMA column c = v'*16 + u', so the neighbours are
-// (m-1, c-1) and (m+1, c+1): one TMEM lane up / down -- a warp shuffle, never leaving the 16-lane
-// half-warp -- and one accumulator column left / right, which the thread already holds.  The outer
-// positions u = 0 and u = 15 of a tile are halo (consumed, not produced), so tiles advance by 14: 112
-// of 128 rows and 14 of 16 columns per key row are productive, and the tensor-core work drops
-// 3 * (14/16)^2 = 2.3x against the dense kernel for identical bf16 scores (same products, fp32 sums).
+// 32 positions wide along u, MMA row m = v*32 + u, MMA column c = v'*32 + u', so the neighbours are
+// (m-1, c-1) and (m+1, c+1): one TMEM lane up / down -- a warp shuffle inside the warp that owns the
+// tile row -- and one accumulator column left / right, which the thread already holds.  The outer
+// positions u = 0 and u = 31 of a tile are halo (consumed, not produced), so tiles advance by 30: 120
+// of 128 rows and 30 of 32 columns per key row are productive, and the tensor-core work drops
+// 3 * (30/32)^2 = 2.6x against the dense kernel for identical bf16 scores (same products, fp32 sums).
+// What bounds the kernel (ncu): the shared-memory crossbar, which carries both the UMMA operand reads
+// (~9 B per accumulator entry) and the shuffles (2 x 4 B per entry) -- not the tensor pipe (55 % active).
 //
 // Operand layout: the same channel-group-planar bf16 images as the dense kernel ([16][Vpad][Upad][8],
-// zero border).  A tile row is exactly 16 positions x 16 B = 256 B, so the canonical no-swizzle
+// zero border).  A tile row is exactly 32 positions x 16 B = 512 B, so the canonical no-swizzle
 // K-major core matrices (8 rows x 16 B) of MMA rows 8g..8g+7 sit at g*128 B: SBO = 128 B, LBO = one
-// channel-group plane of the tile, tap tv = start address + tv*256 B.  One TMA box per operand tile.
+// channel-group plane of the tile, tap tv = start address + tv*512 B.  One TMA box per operand tile.
 //
 // Per CTA (persistent, one per SM, 12 warps):
-//   warp 0    TMA producer (query tile 40 KB resident per query tile, ring of key stages)
-//   warp 1    MMA issuer: per key tile 8 K16-steps x 3 taps = 24 tcgen05.mma (M=128, N=16*Ny)
+//   warp 0    TMA producer (query tile 48 KB resident per query tile, ring of key stages)
+//   warp 1    MMA issuer: per key tile 8 K16-steps x 3 taps = 24 tcgen05.mma (M=128, N=32*Ny)
 //   warp 2    TMEM allocator (2 x 256 columns, double-buffered accumulators)
-//   warps 4-11 epilogue, two groups of four: group h handles key rows [h*ceil(Ny/2), ...) of every tile and
-//             keeps its own top-k list per query (the rescoring merges lists)
+//   warps 4-11 epilogue, two groups of four (warp % 4 = the tile row v it owns): group h handles key rows
+//             [h*ceil(Ny/2), ...) of every tile and keeps its own top-k list per query (the rescoring merges lists)
 #include <cuda.h>
 
 #include "spei_common.cuh"
@@ -35,12 +37,12 @@
 namespace spei {
 
 constexpr int kSThreads = 384;
-constexpr uint32_t kSRowBytes = kSBoxU * 16;                                  // 256 B
+constexpr uint32_t kSRowBytes = kSBoxU * 16;                                  // 512 B
 constexpr uint32_t kSSBO = 128;                                               // 8 positions x 16 B
-constexpr uint32_t kSQRows = kSQTileV + 2;                                    // 10
-constexpr uint32_t kSQLBO = kSQRows * kSRowBytes;                             // 2560
-constexpr uint32_t kSQTileBytes = kCG * kSQLBO;                               // 40960
-constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       // 18432
+constexpr uint32_t kSQRows = kSQTileV + 2;                                    // 6
+constexpr uint32_t kSQLBO = kSQRows * kSRowBytes;                             // 3072
+constexpr uint32_t kSQTileBytes = kCG * kSQLBO;                               // 49152
+constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       // 20480
 constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
 constexpr uint32_t kSNumBars = 2 * kStages + 6;
 constexpr uint32_t kSRkOffset = kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
@@ -115,7 +117,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
         const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
         for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
+          mbar_wait_parked(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
           mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes);
           tma_load_4d(sK + stage * kSStageBytesMax, &tmk, bar_full + 8 * stage, ktu * kSTileU * 8, ktv * p.Ny, (int)(s4 * kCGS),
                       ix.item * p.rf + f);
@@ -136,11 +138,11 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           ++qused;
         }
         const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
-        mbar_wait(bar_tempty + 8 * acc, (use & 1u) ^ 1u, p.error_flag);
+        mbar_wait_parked(bar_tempty + 8 * acc, (use & 1u) ^ 1u, p.error_flag);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kSAccCols;
         for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
-          mbar_wait(bar_full + 8 * stage, phase, p.error_flag);
+          mbar_wait_parked(bar_full + 8 * stage, phase, p.error_flag);
           tc_fence_after();
           const uint32_t kbase = sK + stage * kSStageBytesMax;
 #pragma unroll
@@ -163,26 +165,26 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
-    const int ew = (warp - 4) & 3;        // TMEM lane quarter this warp may read (= warp % 4)
+    const int ew = (warp - 4) & 3;        // TMEM lane quarter this warp may read (= warp % 4) = tile row v
     const int half = (warp - 4) >> 2;     // which half of a tile's key rows
-    const int m = ew * 32 + lane;         // MMA row: query (qu = m % 16, qv = m / 16) of the tile
-    const int qu = m & 15, qv = m >> 4;
+    const int m = ew * 32 + lane;         // MMA row: query (qu = lane, qv = ew) of the tile
+    const int qu = lane, qv = ew;
     const int r_lo = half == 0 ? 0 : (p.Ny + 1) / 2, r_hi = half == 0 ? (p.Ny + 1) / 2 : p.Ny;
     float tv[kTopK];
     int ti[kTopK];
     uint32_t tile_i = 0;
     long long qlin = -1;
     float winq = 0.f;
-    float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * 128;  // this warp's key norms: [rows][16]
-    // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=8 rows][16] reciprocal norms
+    float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * 128;  // this warp's key norms: [<=4 rows][32]
+    // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=4 rows][32] reciprocal norms
     auto rk_prefetch = [&](const PairIdx ix, float2 (&pre)[2]) {
       const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
       const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
       const float* base = p.rkpad + ((size_t)(ix.item * p.rf + f) * p.VkT + ktv * p.Ny + r_lo) * p.UkP + ktu * kSTileU;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int e2 = lane + 32 * j, row = e2 >> 3;
-        pre[j] = (r_lo + row) < r_hi ? __ldg(reinterpret_cast<const float2*>(base + (size_t)row * p.UkP) + (e2 & 7))
+        const int e2 = lane + 32 * j, row = e2 >> 4;
+        pre[j] = (r_lo + row) < r_hi ? __ldg(reinterpret_cast<const float2*>(base + (size_t)row * p.UkP) + (e2 & 15))
                                      : make_float2(0.f, 0.f);
       }
     };
@@ -207,55 +209,83 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       reinterpret_cast<float2*>(rk_s)[lane + 32] = pre[1];
       __syncwarp();
       if (pp + 1 < pe) rk_prefetch(next_pair(ix, p.QT, p.KT), pre);
-      mbar_wait(bar_tfull + 8 * acc, use & 1u, p.error_flag);
+      mbar_wait_parked(bar_tfull + 8 * acc, use & 1u, p.error_flag);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kSAccCols + ((uint32_t)(ew * 32) << 16);
 
-      uint32_t a[16];
-      if (r_lo < r_hi) tc_ld16(taddr + r_lo * 16, a);
+      // One key row (32 accumulator columns = two TMEM loads) per iteration.
+      uint32_t a[16], c[16];
+      if (r_lo < r_hi) {
+        tc_ld16(taddr + r_lo * 32, a);
+        tc_ld16(taddr + r_lo * 32 + 16, c);
+      }
+#pragma unroll 1
       for (int r = r_lo; r < r_hi; ++r) {
         tc_wait_ld();
-        float d[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(a[i]);
         if (p.debug_acc && pp == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) p.debug_acc[(size_t)m * kSAccCols + r * 16 + i] = d[i];
+          for (int i = 0; i < 16; ++i) {
+            p.debug_acc[(size_t)m * kSAccCols + r * 32 + i] = __uint_as_float(a[i]);
+            p.debug_acc[(size_t)m * kSAccCols + r * 32 + 16 + i] = __uint_as_float(c[i]);
+          }
         }
-        if (r + 1 < r_hi) tc_ld16(taddr + (r + 1) * 16, a);  // refill a[] asynchronously while d[] is processed
-        // sum of the three u taps: (m-1, c-1) + (m, c) + (m+1, c+1), scaled by the key's reciprocal norm
-        float v[16];
-        v[0] = -INFINITY; v[15] = -INFINITY;  // halo columns: keys of the neighbouring tiles
-        float rkr[16];
+        // sum of the three u taps: (m-1, col-1) + (m, col) + (m+1, col+1).  Columns 0 and 31 are halo (their sums
+        // are computed on garbage neighbours and never looked at); packed f32x2 adds on the load's register pairs.
+        float s[32];
+        {
+          float x[32], up[32], dn[32];
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 t4 = reinterpret_cast<const float4*>(rk_s + (r - r_lo) * 16)[i4];  // broadcast read
-          rkr[4 * i4] = t4.x; rkr[4 * i4 + 1] = t4.y; rkr[4 * i4 + 2] = t4.z; rkr[4 * i4 + 3] = t4.w;
-        }
+          for (int i = 0; i < 16; ++i) { x[i] = __uint_as_float(a[i]); x[16 + i] = __uint_as_float(c[i]); }
+          up[0] = 0.f; dn[0] = 0.f; up[31] = 0.f; dn[31] = 0.f;
 #pragma unroll
-        for (int i = 1; i < 15; ++i) {
-          const float up = __shfl_up_sync(0xffffffffu, d[i - 1], 1);
-          const float dn = __shfl_down_sync(0xffffffffu, d[i + 1], 1);
-          v[i] = ((up + dn) + d[i]) * rkr[i];  // NaN for keys outside the image
+          for (int i = 1; i < 31; ++i) {
+            up[i] = __shfl_up_sync(0xffffffffu, x[i - 1], 1);
+            dn[i] = __shfl_down_sync(0xffffffffu, x[i + 1], 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float t0, t1;
+            fadd2(t0, t1, up[i], up[i + 1], dn[i], dn[i + 1]);
+            fadd2(s[i], s[i + 1], t0, t1, x[i], x[i + 1]);
+          }
         }
-        float mx = fmaxf(fmaxf(fmaxf(v[1], v[2]), fmaxf(v[3], v[4])), fmaxf(fmaxf(v[5], v[6]), fmaxf(v[7], v[8])));
-        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(v[9], v[10]), fmaxf(v[11], v[12])), fmaxf(v[13], v[14])));
+        if (r + 1 < r_hi) {  // a[], c[] are consumed: refill while the scores are examined
+          tc_ld16(taddr + (r + 1) * 32, a);
+          tc_ld16(taddr + (r + 1) * 32 + 16, c);
+        }
+        float v[32];
+        const float* rkr = rk_s + (r - r_lo) * 32;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 t4 = reinterpret_cast<const float4*>(rkr)[i4];  // broadcast reads
+          fmul2(v[4 * i4], v[4 * i4 + 1], s[4 * i4], s[4 * i4 + 1], t4.x, t4.y);  // NaN for keys outside the image
+          fmul2(v[4 * i4 + 2], v[4 * i4 + 3], s[4 * i4 + 2], s[4 * i4 + 3], t4.z, t4.w);
+        }
+        float mxa = fmaxf(fmaxf(fmaxf(v[1], v[2]), fmaxf(v[3], v[4])), fmaxf(fmaxf(v[5], v[6]), fmaxf(v[7], v[8])));
+        mxa = fmaxf(mxa, fmaxf(fmaxf(fmaxf(v[9], v[10]), fmaxf(v[11], v[12])), fmaxf(fmaxf(v[13], v[14]), v[15])));
+        float mxc = fmaxf(fmaxf(fmaxf(v[16], v[17]), fmaxf(v[18], v[19])), fmaxf(fmaxf(v[20], v[21]), fmaxf(v[22], v[23])));
+        mxc = fmaxf(mxc, fmaxf(fmaxf(fmaxf(v[24], v[25]), fmaxf(v[26], v[27])), fmaxf(fmaxf(v[28], v[29]), v[30])));
         const float thr = fmaxf(tv[kTopK - 1], tv[0] - winq);
-        if (qlin >= 0 && mx > thr) {
+        if (qlin >= 0 && fmaxf(mxa, mxc) > thr) {
+          // compact slow path: bit mask of the qualifying columns (halo columns 0 / 31 excluded), then one sorted
+          // insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
           unsigned msk = 0;
 #pragma unroll
-          for (int i = 1; i < 15; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
+          for (int i = 1; i < 31; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
           while (msk) {
             const int i = __ffs(msk) - 1;
             msk &= msk - 1;
-            float s8[8], s4[4], s2[2];
+            // 32-way register select as a 5-level tree on the bits of i
+            float s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s8[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+            for (int j = 0; j < 16; ++j) s16[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s4[j] = (i & 2) ? s8[2 * j + 1] : s8[2 * j];
+            for (int j = 0; j < 8; ++j) s8[j] = (i & 2) ? s16[2 * j + 1] : s16[2 * j];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) s2[j] = (i & 4) ? s4[2 * j + 1] : s4[2 * j];
-            float x = (i & 8) ? s2[1] : s2[0];
+            for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[2 * j + 1] : s8[2 * j];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) s2[j] = (i & 8) ? s4[2 * j + 1] : s4[2 * j];
+            float x = (i & 16) ? s2[1] : s2[0];
             if (x > fmaxf(tv[kTopK - 1], tv[0] - winq)) {
               int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku0 + i, kv0 + r, p.Wr);
 #pragma unroll

@@ -20,12 +20,12 @@ constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA 
 #define SPEI_TOPK 16
 #endif
 constexpr int kTopK = SPEI_TOPK;  // bf16-pass candidates kept per query per key segment (multiple of 4)
-// tap-sharing search (relevance_tcs.cu): tiles are 16 wide along u (14 interior + a 1-pixel halo each side,
-// the u taps are summed in the epilogue), queries 8 rows, keys up to 16 rows
-constexpr int kSTileU = 14;       // interior tile extent along u
-constexpr int kSBoxU = 16;        // shared-memory tile extent along u = one 256-byte row
-constexpr int kSQTileV = 8;       // query tile: 16 x 8 positions = 128 MMA rows (112 of them interior)
-constexpr int kSMaxNy = 16;       // key tile: 16 x Ny positions = up to 256 MMA columns
+// tap-sharing search (relevance_tcs.cu): tiles are 32 wide along u (30 interior + a 1-position halo each side,
+// the u taps are summed in the epilogue), queries 4 rows, keys up to 8 rows
+constexpr int kSTileU = 30;       // interior tile extent along u
+constexpr int kSBoxU = 32;        // shared-memory tile extent along u = one 512-byte row = one warp of TMEM lanes
+constexpr int kSQTileV = 4;       // query tile: 32 x 4 positions = 128 MMA rows (120 of them interior)
+constexpr int kSMaxNy = 8;        // key tile: 32 x Ny positions = up to 256 MMA columns
 constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
 constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight)
 

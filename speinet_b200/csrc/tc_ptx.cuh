@@ -31,6 +31,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the waiting warp is parked by the hardware instead of burning
+// issue slots that the epilogue warps of the same SM sub-partition need
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 0xfu) == 0) {
+      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
+      if (clock64() - t0 > 4000000000ll) {
+        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
+        return;
+      }
+    }
+  }
+}
+// packed fp32 pairs (sm_100 FADD2 / FMUL2): one issue slot for two lanes of arithmetic
+__device__ __forceinline__ void fadd2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}"
+      : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}"
+      : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // Bounded wait: a protocol bug must surface as an error code, not as a hung GPU.  On a ~2 s timeout the
 // waiter records which barrier starved in *error_flag; from then on every wait in the grid returns
 // immediately, so the kernel drains (with garbage results) and the host can read the code back.

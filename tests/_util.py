@@ -67,8 +67,8 @@ def expected_debug_tile(q, k, info):
 
 def expected_debug_tile_tcs(q, k, info):
     """Tap-sharing kernel (relevance_tcs.cu): raw accumulator D of query tile 0 x key tile 0 = the bf16-operand dot
-    over the 3 taps along v and the 128 channels.  Row m = (v = m // 16, u = m % 16 - 1), column c likewise for the
-    key tile (u = -1 and u = 14 are halo positions; positions outside the image contribute zeros)."""
+    over the 3 taps along v and the 128 channels.  Row m = (v = m // 32, u = m % 32 - 1), column c likewise for the
+    key tile (u = -1 and u = 30 are halo positions; positions outside the image contribute zeros)."""
     qb = bf16_round(q[0]).astype(np.float64)
     kb = bf16_round(k[0]).astype(np.float64)
 
@@ -76,20 +76,20 @@ def expected_debug_tile_tcs(q, k, info):
         C, H, W = img.shape
         img_uv = img if orient == 0 else img.transpose(0, 2, 1)   # [C, V, U]
         V, Uu = img_uv.shape[1:]
-        pad = np.zeros((C, rows + 2, 16))
+        pad = np.zeros((C, rows + 2, 32))
         for vv in range(-1, rows + 1):
-            for uu in range(-1, 15):
+            for uu in range(-1, 31):
                 if 0 <= vv < V and 0 <= uu < Uu:
                     pad[:, vv + 1, uu + 1] = img_uv[:, vv, uu]
-        out = np.zeros((rows * 16, C * 3))
-        for m in range(rows * 16):
-            v, ub = m // 16, m % 16
+        out = np.zeros((rows * 32, C * 3))
+        for m in range(rows * 32):
+            v, ub = m // 32, m % 32
             out[m] = pad[:, v:v + 3, ub].reshape(-1)
         return out
 
-    A = vcols(qb, info["q_orient"], 8)
+    A = vcols(qb, info["q_orient"], 4)
     B = vcols(kb, info["k_orient"], info["k_Ny"])
-    return A @ B.T  # [128, 16*Ny]
+    return A @ B.T  # [128, 32*Ny]
 
 
 def run_search(q, k, search=_lib.SEARCH_TC, eps=0.0):
