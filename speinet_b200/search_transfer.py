@@ -59,7 +59,7 @@ def workspace_bytes(shape: _lib.SpeiShape) -> int:
 
 def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: TensorOrList = None,
                     ref_lv2: TensorOrList = None, ref_lv3: TensorOrList = None, *, fold_mode: str = "cuda",
-                    search: str = "tc", eps: float = 0.0):
+                    search: str = "tcs", eps: float = 0.0):
     """Functional form.  Returns (S, T_lv3, T_lv2, T_lv1, arg[int64 N x L], stats[int32 x 4]).
     Pyramid levels passed as None are skipped (their T is None)."""
     lib = _lib.load()
@@ -105,7 +105,7 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
 class SearchTransfer(nn.Module):
     """Same surface as the reference class (SearchTransfer.py:7-51)."""
 
-    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tc", eps: float = 0.0):
+    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tcs", eps: float = 0.0):
         super().__init__()
         # never used in forward, exactly as in the reference (:10-11); kept for strict checkpoint loading
         self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
@@ -137,7 +137,7 @@ class SelfTransfer(nn.Module):
     same kernels with keys = query transposed and flipped (:59) and no pyramid; the cheap
     bicubic + 1x1-conv transfers (:70-76) stay PyTorch ops, as the scope table says."""
 
-    def __init__(self, n_feat: int = 32, search: str = "tc", eps: float = 0.0):
+    def __init__(self, n_feat: int = 32, search: str = "tcs", eps: float = 0.0):
         super().__init__()
         self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
         self.search2 = nn.Conv2d(n_feat * 2, n_feat, kernel_size=1, stride=1, padding=0)

@@ -9,7 +9,7 @@ import torch
 from speinet_b200 import _lib
 
 
-def make_shape(n, h, w, hr, wr, rf=1, fold_mode=_lib.FOLD_CUDA, search=_lib.SEARCH_TC, eps=0.0):
+def make_shape(n, h, w, hr, wr, rf=1, fold_mode=_lib.FOLD_CUDA, search=_lib.SEARCH_TCS, eps=0.0):
     return _lib.SpeiShape(n=n, h=h, w=w, hr=hr, wr=wr, rf=rf, c3=128, c2=64, c1=32, fold_mode=fold_mode,
                           search=search, eps=eps)
 
@@ -92,7 +92,7 @@ def expected_debug_tile_tcs(q, k, info):
     return A @ B.T  # [128, 32*Ny]
 
 
-def run_search(q, k, search=_lib.SEARCH_TC, eps=0.0):
+def run_search(q, k, search=_lib.SEARCH_TCS, eps=0.0):
     """Stage + relevance only, through the C-ABI.  q [N,128,H,W], k [N,Rf,128,Hr,Wr] CUDA fp32.
     Returns (S [N,1,H,W], arg32 [N,L], stats[4], error_flag)."""
     lib = _lib.load()

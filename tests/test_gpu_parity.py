@@ -47,21 +47,25 @@ def test_torch_cuda_divides_by_multiplying_reciprocal():
 
 
 # ------------------------------------------------------------------ (a)+(b) search ---------------
-@pytest.mark.parametrize("search", ["tc", "exact"])
+SEARCH_MODES = {"tcs": _lib.SEARCH_TCS, "tc": _lib.SEARCH_TC, "exact": _lib.SEARCH_EXACT}
+TC_MODES = ["tcs", "tc"]  # the two tcgen05 candidate passes: tap-sharing (default) and dense
+
+
+@pytest.mark.parametrize("search", ["tcs", "tc", "exact"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_search_matches_reference_golden(golden, name, search):
     g = golden(name)
     q, k = g["q"], g["ref_lv3"]
-    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous(),
-                                         search=_lib.SEARCH_TC if search == "tc" else _lib.SEARCH_EXACT)
+    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous(), search=SEARCH_MODES[search])
     assert flag == 0
     assert_indices_agree(q, k, arg32.cpu().numpy(), g["arg"])
     np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
 
 
-def test_edge_semantics_zero_patch_and_duplicate_keys(golden):
+@pytest.mark.parametrize("search", TC_MODES)
+def test_edge_semantics_zero_patch_and_duplicate_keys(golden, search):
     g = golden("st_edge")
-    S, arg32, _, _ = U.run_search(cu(g["q"]), cu(g["ref_lv3"]).unsqueeze(1).contiguous())
+    S, arg32, _, _ = U.run_search(cu(g["q"]), cu(g["ref_lv3"]).unsqueeze(1).contiguous(), search=SEARCH_MODES[search])
     arg = arg32.cpu().numpy().reshape(8, 16)
     S = S.cpu().numpy()[0, 0]
     assert (arg[0:2, 0:2] == 0).all() and (S[0:2, 0:2] == 0).all()      # zero query patch -> index 0, S = 0
@@ -69,8 +73,12 @@ def test_edge_semantics_zero_patch_and_duplicate_keys(golden):
     assert np.array_equal(arg, g["arg"].reshape(8, 16))
 
 
-@pytest.mark.parametrize("shape", [(1, 37, 50, 29, 44, 1), (2, 24, 40, 24, 40, 1), (1, 33, 21, 40, 35, 2), (1, 64, 64, 64, 64, 1)])
-def test_tc_search_matches_oracle_random(shape):
+# grids around the tile sizes of both kernels (8 / 16 dense, 30 / 4 / 8 tap-sharing), ragged, tiny, two frames
+@pytest.mark.parametrize("search", TC_MODES)
+@pytest.mark.parametrize("shape", [(1, 37, 50, 29, 44, 1), (2, 24, 40, 24, 40, 1), (1, 33, 21, 40, 35, 2), (1, 64, 64, 64, 64, 1),
+                                   (1, 30, 30, 31, 61, 1), (1, 4, 60, 9, 29, 1), (1, 1, 1, 1, 1, 1), (1, 2, 3, 1, 7, 1),
+                                   (1, 5, 91, 17, 32, 2)])
+def test_tc_search_matches_oracle_random(shape, search):
     n, h, w, hr, wr, rf = shape
     rng = np.random.default_rng(hash(shape) % (1 << 31))
     q = (rng.standard_normal((n, 128, h, w)) * 0.2).astype(np.float32)
@@ -78,13 +86,14 @@ def test_tc_search_matches_oracle_random(shape):
     qu = oracle.l2_normalize(oracle.unfold(q, 3, 1, 1), axis=1)
     ku = oracle.l2_normalize(np.concatenate([oracle.unfold(k, 3, 1, 1) for k in ks], axis=2), axis=1)
     want_S, want_arg = oracle.relevance(qu, ku)
-    S, arg32, stats, flag = U.run_search(cu(q), torch.stack([cu(k) for k in ks], dim=1).contiguous())
+    S, arg32, stats, flag = U.run_search(cu(q), torch.stack([cu(k) for k in ks], dim=1).contiguous(), search=SEARCH_MODES[search])
     assert flag == 0
     assert_indices_agree(q, ks, arg32.cpu().numpy(), want_arg)
     np.testing.assert_allclose(S.cpu().numpy().reshape(n, -1), want_S, rtol=RTOL_S, atol=1e-6)
 
 
-def test_tc_search_smooth_features_many_near_candidates():
+@pytest.mark.parametrize("search", TC_MODES)
+def test_tc_search_smooth_features_many_near_candidates(search):
     """Image-like (spatially smooth) features put many keys inside the candidate window; the
     saturated-list -> exhaustive fp32 fallback must keep the result exact."""
     rng = np.random.default_rng(9)
@@ -95,19 +104,21 @@ def test_tc_search_smooth_features_many_near_candidates():
     qu = oracle.l2_normalize(oracle.unfold(q, 3, 1, 1), axis=1)
     ku = oracle.l2_normalize(oracle.unfold(k, 3, 1, 1), axis=1)
     want_S, want_arg = oracle.relevance(qu, ku)
-    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous())
+    S, arg32, stats, flag = U.run_search(cu(q), cu(k).unsqueeze(1).contiguous(), search=SEARCH_MODES[search])
     assert flag == 0
     assert_indices_agree(q, k, arg32.cpu().numpy(), want_arg)
     np.testing.assert_allclose(S.cpu().numpy().reshape(1, -1), want_S, rtol=RTOL_S, atol=1e-6)
 
 
-def test_debug_tile_accumulator_matches_bf16_dot():
-    """The raw tcgen05 accumulator of (query tile 0, key tile 0) equals the bf16-operand dot products."""
+@pytest.mark.parametrize("search", TC_MODES)
+def test_debug_tile_accumulator_matches_bf16_dot(search):
+    """The raw tcgen05 accumulator of (query tile 0, key tile 0) equals the bf16-operand dot products
+    (all nine taps for the dense kernel, the three v taps for the tap-sharing kernel)."""
     rng = np.random.default_rng(1)
     q = rng.standard_normal((1, 128, 20, 24)).astype(np.float32)
     k = rng.standard_normal((1, 128, 20, 24)).astype(np.float32)
-    acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous())
-    want = U.expected_debug_tile(q, k, info)
+    acc, info, flag = U.run_debug_tile(cu(q), cu(k).unsqueeze(1).contiguous(), search=SEARCH_MODES[search])
+    want = (U.expected_debug_tile_tcs if search == "tcs" else U.expected_debug_tile)(q, k, info)
     assert flag == 0
     np.testing.assert_allclose(acc[:, :want.shape[1]], want, rtol=0, atol=2e-3)
 
@@ -322,13 +333,14 @@ def test_full_size_720p_properties():
     assert st.last_stats.cpu().tolist()[0] == 0
 
 
-def test_full_size_720p_random_subset_vs_exhaustive_fp32():
-    """TC path vs the exhaustive fp32 CUDA-core search on the same staged operands, 720p, random data."""
+@pytest.mark.parametrize("search", TC_MODES)
+def test_full_size_720p_random_subset_vs_exhaustive_fp32(search):
+    """TC paths vs the exhaustive fp32 CUDA-core search on the same staged operands, 720p, random data."""
     torch.manual_seed(2)
     h, w = 180, 320
     q = torch.randn(1, 128, h, w, device="cuda") * 0.2
     k = (torch.randn(1, 1, 128, h, w, device="cuda") * 0.04).contiguous()
-    S_tc, a_tc, stats, flag = U.run_search(q, k, search=_lib.SEARCH_TC)
+    S_tc, a_tc, stats, flag = U.run_search(q, k, search=SEARCH_MODES[search])
     S_ex, a_ex, _, _ = U.run_search(q, k, search=_lib.SEARCH_EXACT)
     assert flag == 0
     diff = (a_tc != a_ex)
