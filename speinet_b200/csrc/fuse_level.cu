@@ -15,6 +15,8 @@
 // (error ~2^-21 per product, i.e. fp32 class).  Operands are streamed through a double-buffered
 // cp.async pipeline; shared-memory pitches (W: K-chunk+4, X: 128+8 floats) make every mma.sync
 // fragment load bank-conflict free.
+#include <cstdlib>
+
 #include "spei_common.cuh"
 
 namespace spei {
@@ -59,10 +61,13 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// x = hi + lo with hi = x truncated to TF32 (top 19 bits) and lo = x - hi, which is exact in fp32.  The tensor
+// core ignores the 13 low mantissa bits of a .tf32 operand, so lo needs no conversion either: its own
+// truncation error is 2^-10 |lo| <= 2^-20 |x|.  One LOP3 + one FADD instead of two cvt.rna (the conversion
+// pipe, not the MMA, was what bounded this kernel).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -207,9 +212,14 @@ static int launch_fuse_t(int n, int h, int w, int scale, const float* dec, const
   return SPEI_OK;
 }
 
+int launch_fuse_level_tc(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
+                         const float* weight, const float* bias, float* out, cudaStream_t st);
+
 int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
                       const float* weight, const float* bias, float* out, cudaStream_t st) {
   if (n > 65535) { set_error("fuse_level: n too large"); return SPEI_ERR_ARG; }
+  static const bool legacy = getenv("SPEI_FUSE_MMA_SYNC") != nullptr;  // A/B switch: the mma.sync version below
+  if (!legacy) return launch_fuse_level_tc(n, c, h, w, scale, dec, t, S, weight, bias, out, st);
   const size_t plane = (size_t)h * scale * w * scale;
   const bool vec = (plane % 4) == 0;
 #define FUSE(C_) (vec ? launch_fuse_t<C_, true>(n, h, w, scale, dec, t, S, weight, bias, out, st) \

@@ -1,0 +1,610 @@
+// Kernel (d) on the 5th-generation tensor cores: one fusion line of SPEINet._decode
+// (/root/reference/model/speinet.py:93-94, 96-97, 108-109)
+//
+//     out = dec + (W . cat(dec, T) + b) * bicubic_up(S, scale)
+//
+// as ONE pass over HBM (read dec, read T, write out = 3 x tensor size, the algorithmic minimum).
+// The 1x1 convolution is a skinny GEMM  D[pixel, o] = sum_k X[k, pixel] * W[o, k]  (K = 2C) that must keep
+// fp32 accuracy (1e-4 bar), so it runs as 3xTF32 on tcgen05: x = hi + lo with hi = x truncated to TF32 and
+// lo = x - hi (exact), D ~= Xlo.Whi + Xhi.Wlo + Xhi.Whi with fp32 accumulation in TMEM (dropped term
+// ~2^-22).  M = 128 pixels (one TMEM lane per pixel), N = C output channels, kind::tf32, K = 8 per MMA.
+//
+// The split needs a register pass over the activations anyway, so the producer warps do the layout
+// change at the same time: coalesced loads along pixels (NCHW planes), split, 16-byte stores straight into
+// the canonical no-swizzle K-major UMMA layout (core matrix = 8 rows x 16 B = 8 pixels x 4 channels,
+// rows contiguous: SBO = 128 B, LBO = 128 rows x 16 B).  No TMA, no alignment requirement on the planes.
+//
+// CTA = 160 threads: warps 0-3 produce (thread = pixel; it also owns one weight row) and later run the
+// epilogue (thread = TMEM lane = pixel: every channel store is a coalesced 128-byte row segment), warp 4
+// issues the MMAs.  Three 16-channel stages, loads prefetched one 32-channel set ahead in registers, two to
+// three CTAs per SM.  Versus the mma.sync version this replaces: 87 / 81 / 101 us -> see DESIGN.md.
+#include <cstdlib>
+
+#include "spei_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace spei {
+
+constexpr int kFM = 128;       // pixels per CTA = MMA M
+constexpr int kFKC = 16;       // channels per pipeline stage = 2 MMA K-steps of 8
+constexpr int kFStages = 3;
+constexpr int kFThreads = 160;
+
+__device__ __forceinline__ float ft_cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float ft_cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+// F.interpolate(S, scale_factor, mode='bicubic'): align_corners=False, A=-0.75, border-clamped taps
+// (torch/include/ATen/native/UpSample.h:289-300,400-423)
+__device__ __forceinline__ float ft_bicubic(const float* __restrict__ S, int h, int w, int oy, int ox, float rscale) {
+  const float ry = rscale * (oy + 0.5f) - 0.5f, rx = rscale * (ox + 0.5f) - 0.5f;
+  const float fy = floorf(ry), fx = floorf(rx);
+  const int iy = (int)fy, ix = (int)fx;
+  const float ty = ry - fy, tx = rx - fx;
+  const float cx[4] = {ft_cubic2(tx + 1.f), ft_cubic1(tx), ft_cubic1(1.f - tx), ft_cubic2(2.f - tx)};
+  const float cy[4] = {ft_cubic2(ty + 1.f), ft_cubic1(ty), ft_cubic1(1.f - ty), ft_cubic2(2.f - ty)};
+  float rows[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(iy - 1 + i, 0), h - 1);
+    const float* r = S + (size_t)yy * w;
+    const float v0 = __ldg(r + min(max(ix - 1, 0), w - 1)), v1 = __ldg(r + min(max(ix, 0), w - 1));
+    const float v2 = __ldg(r + min(max(ix + 1, 0), w - 1)), v3 = __ldg(r + min(max(ix + 2, 0), w - 1));
+    rows[i] = v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3];
+  }
+  return rows[0] * cy[0] + rows[1] * cy[1] + rows[2] * cy[2] + rows[3] * cy[3];
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// hi = x truncated to TF32, lo = x - hi (exact; the tensor core ignores lo's 13 low mantissa bits: 2^-20 |x|)
+__device__ __forceinline__ void ft_split4(const float (&x)[4], uint4& hi, uint4& lo) {
+  hi.x = __float_as_uint(x[0]) & 0xffffe000u; hi.y = __float_as_uint(x[1]) & 0xffffe000u;
+  hi.z = __float_as_uint(x[2]) & 0xffffe000u; hi.w = __float_as_uint(x[3]) & 0xffffe000u;
+  lo.x = __float_as_uint(x[0] - __uint_as_float(hi.x)); lo.y = __float_as_uint(x[1] - __uint_as_float(hi.y));
+  lo.z = __float_as_uint(x[2] - __uint_as_float(hi.z)); lo.w = __float_as_uint(x[3] - __uint_as_float(hi.w));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ int g_fuse_watchdog;  // set by a starved barrier wait (bounded waits: a protocol bug must not hang the GPU)
+
+template <int C>
+struct FuseTcSmem {
+  static constexpr uint32_t kALBO = kFM * 16;                 // 2048: stride between 4-channel core-matrix columns of X
+  static constexpr uint32_t kBLBO = C * 16;                   // ... of W
+  static constexpr uint32_t kABytes = (kFKC / 4) * kALBO;     // 8192 per hi / lo tile
+  static constexpr uint32_t kBBytes = (kFKC / 4) * kBLBO;
+  static constexpr uint32_t kStage = 2 * kABytes + 2 * kBBytes;
+  static constexpr uint32_t kBars = kFStages * kStage;        // full[3], empty[3], accfull, tmem slot
+  static constexpr uint32_t kTotal = kBars + 8 * (2 * kFStages + 1) + 16;
+};
+
+// grid: persistent, up to 2 (C = 128) or 3 CTAs per SM; each CTA walks 128-pixel tiles with stride gridDim.x
+template <int C>
+__global__ void __launch_bounds__(kFThreads, C == 128 ? 2 : 3)
+fuse_level_tc_kernel(const float* __restrict__ dec, const float* __restrict__ tt, const float* __restrict__ S,
+                     const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out, int n_items,
+                     int h, int w, int scale) {
+  using L = FuseTcSmem<C>;
+  int* error_flag = &g_fuse_watchdog;
+  constexpr int K = 2 * C, NCH = K / kFKC;
+  constexpr uint32_t kCols = C < 32 ? 32 : C;  // TMEM columns (power of two >= 32)
+  extern __shared__ __align__(1024) uint8_t fsmem[];
+  const uint32_t s0 = smem_u32(fsmem);
+  const uint32_t bar_full = s0 + L::kBars, bar_empty = bar_full + 8 * kFStages, bar_acc = bar_empty + 8 * kFStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fsmem + L::kBars + 8 * (2 * kFStages + 1));
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int hs = h * scale, wsz = w * scale;
+  const size_t plane = (size_t)hs * wsz;
+
+  if (t == 0) {
+    for (int s = 0; s < kFStages; ++s) { mbar_init(bar_full + 8 * s, kFM); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long tpi = (long long)((plane + kFM - 1) / kFM), total = tpi * n_items;
+
+  if (warp < 4) {
+    // ============================ producer: thread = pixel (and weight row) ============================
+    const int px = t;
+    const bool wrow = px < C;
+    const float* w_row = weight + (size_t)(wrow ? px : 0) * K;
+
+    struct TileCtx { bool pin; size_t base; float sw; };  // base = offset of (item, channel 0, this pixel)
+    auto make_ctx = [&](long long tile) {
+      TileCtx c;
+      const int n = (int)(tile / tpi);
+      const size_t p = (size_t)(tile - (long long)n * tpi) * kFM + px;
+      c.pin = p < plane;
+      c.base = (size_t)n * C * plane + (c.pin ? p : 0);
+      c.sw = 0.f;  // soft-attention weight of this pixel (bicubic upsampled S), kept in a register for the epilogue
+      if (c.pin) {
+        const int oy = (int)(p / wsz), ox = (int)(p % wsz);
+        const float* S_n = S + (size_t)n * h * w;
+        c.sw = scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : ft_bicubic(S_n, h, w, oy, ox, 1.0f / (float)scale);
+      }
+      return c;
+    };
+
+    // Loads run one 32-channel set (= two pipeline stages) ahead of the stores in a two-set register ring, so
+    // every thread keeps 32 coalesced 4-byte loads in flight (16 KB per CTA) while it splits and stores the
+    // previous set; the first set of the NEXT tile is issued before the epilogue of the current one.  A set
+    // never straddles the dec / T halves of the concatenation (C is a multiple of 32).
+    constexpr int kSet = 2 * kFKC, NSC = K / kSet;
+    auto load_set = [&](const TileCtx& c, int sc, float (&x)[kSet]) {
+      const int ch0 = sc * kSet;
+      const float* src = (ch0 < C ? dec + (size_t)ch0 * plane : tt + (size_t)(ch0 - C) * plane) + c.base;
+#pragma unroll
+      for (int i = 0; i < kSet; ++i) x[i] = c.pin ? __ldg(src + (size_t)i * plane) : 0.f;
+    };
+    // The weight row (L2 resident, 64 bytes per stage) is prefetched one stage ahead (wrapping into the next tile).
+    float4 wnext[kFKC / 4];
+    auto load_w = [&](int kc) {
+      if (kc == NCH) kc = 0;
+#pragma unroll
+      for (int j = 0; j < kFKC / 4; ++j)
+        wnext[j] = wrow ? __ldg(reinterpret_cast<const float4*>(w_row + kc * kFKC) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_set = [&](int g0, int sc, const float (&x)[kSet]) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int kc = 2 * sc + hf, g = g0 + kc, s = g % kFStages;
+        float4 wv[kFKC / 4];
+#pragma unroll
+        for (int j = 0; j < kFKC / 4; ++j) wv[j] = wnext[j];
+        load_w(kc + 1);
+        if (g >= kFStages) mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kFStages - 1) & 1), error_flag);
+        const uint32_t a_hi = s0 + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
+#pragma unroll
+        for (int j = 0; j < kFKC / 4; ++j) {
+          const int e = hf * kFKC + 4 * j;
+          const float x4[4] = {x[e], x[e + 1], x[e + 2], x[e + 3]};
+          uint4 hi, lo;
+          ft_split4(x4, hi, lo);
+          st_shared_v4(a_hi + j * L::kALBO + px * 16, hi);
+          st_shared_v4(a_lo + j * L::kALBO + px * 16, lo);
+          if (wrow) {
+            const float4 w4v = wv[j];
+            const float w4[4] = {w4v.x, w4v.y, w4v.z, w4v.w};
+            ft_split4(w4, hi, lo);
+            st_shared_v4(b_hi + j * L::kBLBO + px * 16, hi);
+            st_shared_v4(b_lo + j * L::kBLBO + px * 16, lo);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA (async proxy)
+        mbar_arrive(bar_full + 8 * s);
+      }
+    };
+
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float xa[kSet], xb[kSet];
+    long long tile = blockIdx.x;
+    TileCtx cur = make_ctx(tile < total ? tile : 0);
+    if (tile < total) { load_set(cur, 0, xa); load_w(0); }
+    int it = 0;
+#pragma unroll 1
+    for (; tile < total; tile += gridDim.x, ++it) {
+      const int g0 = it * NCH;
+#pragma unroll 1
+      for (int sc = 0; sc < NSC; sc += 2) {
+        load_set(cur, sc + 1, xb);
+        store_set(g0, sc, xa);
+        if (sc + 2 < NSC) load_set(cur, sc + 2, xa);
+        store_set(g0, sc + 1, xb);
+      }
+      // next tile: context (bicubic taps) and first set of loads go out before this tile's epilogue
+      const bool more = tile + gridDim.x < total;
+      TileCtx nxt = cur;
+      if (more) { nxt = make_ctx(tile + gridDim.x); load_set(nxt, 0, xa); }
+
+      // ---------------- epilogue: thread = TMEM lane = pixel ----------------
+      mbar_wait(bar_acc, (uint32_t)(it & 1), error_flag);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        uint32_t a[16];
+        tc_ld16(taddr + c0, a);
+        float dv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dv[i] = cur.pin ? __ldg(dec + cur.base + (size_t)(c0 + i) * plane) : 0.f;  // residual (L2 hit)
+        tc_wait_ld();
+        if (cur.pin) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            out[cur.base + (size_t)(c0 + i) * plane] = dv[i] + (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * cur.sw;
+        }
+      }
+      tc_fence_before();  // accumulator reads are complete before this thread's next barrier arrival lets the MMA overwrite it
+      cur = nxt;
+    }
+  } else if (lane == 0) {
+    // ======================================== MMA issuer ========================================
+    // kind::tf32 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = tf32 (bits 7-9, 10-12 = 2), K-major both,
+    // N >> 3 at bits 17-22, M >> 4 at bits 24-28
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
+    int g = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kc = 0; kc < NCH; ++kc, ++g) {
+        const int s = g % kFStages;
+        mbar_wait(bar_full + 8 * s, (uint32_t)((g / kFStages) & 1), error_flag);
+        tc_fence_after();
+        const uint32_t a_hi = s0 + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
+#pragma unroll
+        for (uint32_t kk = 0; kk < kFKC / 8; ++kk) {
+          const uint64_t dah = umma_desc_kmajor(a_hi + kk * 2 * L::kALBO, L::kALBO, 128);
+          const uint64_t dal = umma_desc_kmajor(a_lo + kk * 2 * L::kALBO, L::kALBO, 128);
+          const uint64_t dbh = umma_desc_kmajor(b_hi + kk * 2 * L::kBLBO, L::kBLBO, 128);
+          const uint64_t dbl = umma_desc_kmajor(b_lo + kk * 2 * L::kBLBO, L::kBLBO, 128);
+          tc_mma_tf32(tmem_base, dal, dbh, idesc, (kc | kk) != 0);  // small terms first
+          tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          tc_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        tc_commit(bar_empty + 8 * s);
+      }
+      tc_commit(bar_acc);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed version (planes whose byte stride is a multiple of 16, i.e. plane % 4 == 0 -- every shape the model
+// produces).  Plain 4-byte loads cap the bytes a warp keeps in flight (the LDG version above reaches ~2.5 TB/s),
+// so here one elected thread streams raw [16 channel][128 pixel] fp32 boxes of dec / T through a 4-deep TMA
+// ring (32-40 KB of activations in flight per CTA; the 16-column weight slab of each stage rides in the same ring); the converter warps read a box back with thread = pixel
+// (conflict-free), split and re-store it as hi / lo UMMA tiles; the accumulator is double-buffered in TMEM and
+// drained by separate epilogue warps through a shared-memory staging tile, so that the residual read and the
+// output write are 16-byte accesses of whole 512-byte rows and overlap the next tile's conversion.
+//   warps 0-3  convert     warp 4  MMA issuer (+ TMEM alloc)     warp 5  TMA producer     warps 6-9  epilogue
+// ---------------------------------------------------------------------------------------------------------
+#ifdef SPEI_FUSE_SPIN
+#define FUSE_WAIT mbar_wait_spin
+#else
+#define FUSE_WAIT mbar_wait
+#endif
+constexpr uint32_t kFRawBytes = kFKC * kFM * 4;           // 8192: one raw activation box
+constexpr int kFOutCh = 16;                               // channels per epilogue staging pass
+constexpr int kFTmaThreads = 320;
+
+template <int C>
+struct FuseTmaSmem {
+  using L = FuseTcSmem<C>;
+  static constexpr int kFRaw = C == 128 ? 5 : 4;                  // raw TMA ring depth (C = 128: one CTA per SM, deeper rings)
+  static constexpr int kFU = C == 128 ? 3 : 2;                    // UMMA-layout ring depth
+  static constexpr int kCtasPerSm = C == 128 ? 1 : 2;
+  static constexpr uint32_t kRaw = 0;
+  static constexpr uint32_t kWBox = C * kFKC * 4;                 // raw weight box [C rows][16 k] fp32
+  static constexpr uint32_t kRawStage = kFRawBytes + kWBox;       // X box + W box per TMA stage
+  static constexpr uint32_t kUmma = kFRaw * kRawStage;
+  static constexpr uint32_t kOut = kUmma + kFU * L::kStage;
+  static constexpr uint32_t kBars = kOut + 2 * kFOutCh * kFM * 4;   // (staging tile double-buffered) raw_full[4] raw_empty[4] u_full[2] u_empty[2] acc_full[2] acc_empty[2]
+  static constexpr uint32_t kNumBars = 2 * kFRaw + 2 * kFU + 4;
+  static constexpr uint32_t kTotal = kBars + 8 * kNumBars + 16;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kFTmaThreads, FuseTmaSmem<C>::kCtasPerSm)
+fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_constant__ CUtensorMap tm_t,
+                      const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ dec, const float* __restrict__ S, const float* __restrict__ weight,
+                      const float* __restrict__ bias, float* __restrict__ out, int n_items, int h, int w, int scale) {
+  using L = FuseTcSmem<C>;
+  using SM = FuseTmaSmem<C>;
+  constexpr int kFRaw = SM::kFRaw, kFU = SM::kFU;
+  int* error_flag = &g_fuse_watchdog;
+  constexpr int K = 2 * C, NCH = K / kFKC;
+  constexpr uint32_t kCols = 2 * C < 32 ? 32 : 2 * C;   // two accumulators
+  extern __shared__ __align__(1024) uint8_t fsmem[];
+  const uint32_t s0 = smem_u32(fsmem);
+  const uint32_t bar_rfull = s0 + SM::kBars, bar_rempty = bar_rfull + 8 * kFRaw, bar_ufull = bar_rempty + 8 * kFRaw,
+                 bar_uempty = bar_ufull + 8 * kFU, bar_afull = bar_uempty + 8 * kFU, bar_aempty = bar_afull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fsmem + SM::kBars + 8 * SM::kNumBars);
+  float* ostage = reinterpret_cast<float*>(fsmem + SM::kOut);   // [2][16 ch][128 px]
+  const float* raw = reinterpret_cast<const float*>(fsmem + SM::kRaw);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int hs = h * scale, wsz = w * scale;
+  const size_t plane = (size_t)hs * wsz;
+  const long long tpi = (long long)((plane + kFM - 1) / kFM), total = tpi * n_items;
+
+  if (t == 0) {
+    for (int s = 0; s < kFRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, kFM); }
+    for (int s = 0; s < kFU; ++s) { mbar_init(bar_ufull + 8 * s, kFM); mbar_init(bar_uempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, kFM); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dec) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_t) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================== convert (thread = pixel; threads < C also convert one weight row) ==================
+    const int px = t;
+    const bool wrow = px < C;
+    long long tile = blockIdx.x;
+    int g = 0;
+#pragma unroll 1
+    for (; tile < total; tile += gridDim.x) {
+#pragma unroll 1
+      for (int kc = 0; kc < NCH; ++kc, ++g) {
+        const int r = g % kFRaw, s = g % kFU;
+        FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kFRaw) & 1), error_flag);
+        const float* rbox = raw + (size_t)r * (SM::kRawStage / 4);
+        float x[kFKC];
+#pragma unroll
+        for (int c = 0; c < kFKC; ++c) x[c] = rbox[c * kFM + px];
+        float4 wv[kFKC / 4];
+#pragma unroll
+        for (int j = 0; j < kFKC / 4; ++j)
+          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // generic-proxy reads must be ordered before the async-proxy (TMA) refill of this box: without this
+        // fence the refill raced with the reads (measured: sporadic wrong tiles at C = 128, where the ring wraps)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_rempty + 8 * r);
+        if (g >= kFU) FUSE_WAIT(bar_uempty + 8 * s, (uint32_t)((g / kFU - 1) & 1), error_flag);
+        const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
+#ifndef SPEI_FUSE_NO_CONV
+#pragma unroll
+        for (int j = 0; j < kFKC / 4; ++j) {
+          const float x4[4] = {x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]};
+          uint4 hi, lo;
+          ft_split4(x4, hi, lo);
+          st_shared_v4(a_hi + j * L::kALBO + px * 16, hi);
+          st_shared_v4(a_lo + j * L::kALBO + px * 16, lo);
+          if (wrow) {
+            const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+            ft_split4(w4, hi, lo);
+            st_shared_v4(b_hi + j * L::kBLBO + px * 16, hi);
+            st_shared_v4(b_lo + j * L::kBLBO + px * 16, lo);
+          }
+        }
+#else
+        if (x[0] == 123.456f && wv[0].x == 3.f) st_shared_v4(a_hi, make_uint4(1, 2, 3, 4));  // keep the loads alive
+#endif
+#ifndef SPEI_FUSE_NO_FENCE2
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> visible to the MMA (async proxy)
+#endif
+        mbar_arrive(bar_ufull + 8 * s);
+      }
+    }
+  } else if (warp == 4) {
+    // ======================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
+      int g = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1;
+        if (it >= 2) FUSE_WAIT(bar_aempty + 8 * ab, (uint32_t)((it / 2 - 1) & 1), error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * C;
+        for (int kc = 0; kc < NCH; ++kc, ++g) {
+          const int s = g % kFU;
+          FUSE_WAIT(bar_ufull + 8 * s, (uint32_t)((g / kFU) & 1), error_flag);
+          tc_fence_after();
+          const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
+#pragma unroll
+          for (uint32_t kk = 0; kk < kFKC / 8; ++kk) {
+            const uint64_t dah = umma_desc_kmajor(a_hi + kk * 2 * L::kALBO, L::kALBO, 128);
+            const uint64_t dal = umma_desc_kmajor(a_lo + kk * 2 * L::kALBO, L::kALBO, 128);
+            const uint64_t dbh = umma_desc_kmajor(b_hi + kk * 2 * L::kBLBO, L::kBLBO, 128);
+            const uint64_t dbl = umma_desc_kmajor(b_lo + kk * 2 * L::kBLBO, L::kBLBO, 128);
+#ifndef SPEI_FUSE_NO_MMA   // (experiment switch: hand-off latency without the MMAs)
+            tc_mma_tf32(d_tmem, dal, dbh, idesc, (kc | kk) != 0);  // small terms first
+            tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+#endif
+          }
+          tc_commit(bar_uempty + 8 * s);
+        }
+        tc_commit(bar_afull + 8 * ab);
+      }
+    }
+  } else if (warp == 5) {
+    // ======================================== TMA producer ========================================
+    if (lane == 0) {
+      int g = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n = (int)(tile / tpi);
+        const int p0 = (int)((tile - (long long)n * tpi) * kFM);
+        for (int kc = 0; kc < NCH; ++kc, ++g) {
+          const int r = g % kFRaw;
+          if (g >= kFRaw) FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kFRaw - 1) & 1), error_flag);
+          mbar_arrive_expect_tx(bar_rfull + 8 * r, SM::kRawStage);
+          const int ch0 = kc * kFKC;
+          tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage, ch0 < C ? &tm_dec : &tm_t, bar_rfull + 8 * r, p0, n * C + (ch0 < C ? ch0 : ch0 - C));
+          tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage + kFRawBytes, &tm_w, bar_rfull + 8 * r, ch0, 0);  // weight columns ch0..ch0+15
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (thread = TMEM lane = pixel) ================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int px = q * 32 + lane;
+    const int te = (warp - 6) * 32 + lane;  // 0..127: cooperative row mapping of the store phase
+    auto soft_weight = [&](long long tile) {  // bicubic upsampled S at this thread's pixel of `tile`
+      const int n = (int)(tile / tpi);
+      const size_t p = (size_t)(tile - (long long)n * tpi) * kFM + px;
+      if (p >= plane) return 0.f;
+      const int oy = (int)(p / wsz), ox = (int)(p % wsz);
+      const float* S_n = S + (size_t)n * h * w;
+      return scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : ft_bicubic(S_n, h, w, oy, ox, 1.0f / (float)scale);
+    };
+    // residual rows (16-byte loads of whole 512-byte channel rows) are prefetched one staging pass ahead, across
+    // tile boundaries: the epilogue never waits for a load it has just issued
+    const int px4 = (te & 31) * 4;
+    auto load_residual = [&](long long tile_, int c0, float4 (&dv)[kFOutCh / 4]) {
+      const int n = (int)(tile_ / tpi);
+      const size_t p0 = (size_t)(tile_ - (long long)n * tpi) * kFM;
+      const bool rin = tile_ < total && p0 + px4 < plane;
+#pragma unroll
+      for (int k = 0; k < kFOutCh / 4; ++k) {
+        const int ch = (te >> 5) + 4 * k;
+        dv[k] = rin ? __ldg(reinterpret_cast<const float4*>(dec + ((size_t)n * C + c0 + ch) * plane + p0 + px4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    long long tile = blockIdx.x;
+    float sw = tile < total ? soft_weight(tile) : 0.f;
+    float4 dnext[kFOutCh / 4];
+    load_residual(tile, 0, dnext);
+    int it = 0, pass = 0;
+#pragma unroll 1
+    for (; tile < total; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1;
+      const float sw_next = tile + gridDim.x < total ? soft_weight(tile + gridDim.x) : 0.f;  // taps in flight during this tile
+      const int n = (int)(tile / tpi);
+      const size_t p0 = (size_t)(tile - (long long)n * tpi) * kFM;
+      const bool rin = p0 + px4 < plane;
+      FUSE_WAIT(bar_afull + 8 * ab, (uint32_t)((it / 2) & 1), error_flag);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * C + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += kFOutCh, ++pass) {
+        float4 dv[kFOutCh / 4];
+#pragma unroll
+        for (int k = 0; k < kFOutCh / 4; ++k) dv[k] = dnext[k];
+        if (c0 + kFOutCh < C) load_residual(tile, c0 + kFOutCh, dnext); else load_residual(tile + gridDim.x, 0, dnext);
+        float* ost = ostage + (pass & 1) * (kFOutCh * kFM);   // double-buffered staging tile: one barrier per pass
+        uint32_t a[16];
+        tc_ld16(taddr + c0, a);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ost[i * kFM + px] = (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#ifdef SPEI_FUSE_NO_EPI
+        if (rin && dv[0].x == 123.456f)
+#else
+        if (rin)
+#endif
+        {
+#pragma unroll
+          for (int k = 0; k < kFOutCh / 4; ++k) {
+            const int ch = (te >> 5) + 4 * k;
+            const float4 v = *reinterpret_cast<const float4*>(ost + ch * kFM + px4);
+            *reinterpret_cast<float4*>(out + ((size_t)n * C + c0 + ch) * plane + p0 + px4) =
+                make_float4(dv[k].x + v.x, dv[k].y + v.y, dv[k].z + v.z, dv[k].w + v.w);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_aempty + 8 * ab);   // this accumulator may be overwritten by the tile after next
+      sw = sw_next;
+    }
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
+  }
+}
+
+// 2-D map over an NCHW fp32 tensor seen as [n*C rows][plane]; box = 16 channels x 128 pixels
+static int make_plane_map(EncodeTiledFn enc, CUtensorMap* tm, const float* base, size_t rows, size_t plane) {
+  const cuuint64_t dims[2] = {(cuuint64_t)plane, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)plane * 4};
+  const cuuint32_t box[2] = {kFM, kFKC};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
+  return SPEI_OK;
+}
+
+template <int C>
+static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, const float* t, const float* S, const float* weight,
+                             const float* bias, float* out, cudaStream_t st) {
+  const size_t plane = (size_t)h * scale * w * scale;
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  CUtensorMap tmd, tmt, tmw;
+  if ((rc = make_plane_map(enc, &tmd, dec, (size_t)n * C, plane))) return rc;
+  if ((rc = make_plane_map(enc, &tmt, t, (size_t)n * C, plane))) return rc;
+  {  // Conv2d 1x1 weight [C rows][2C] fp32; box = all C rows x 16 input channels
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * C), (cuuint64_t)C};
+    const cuuint64_t strides[1] = {(cuuint64_t)(2 * C) * 4};
+    const cuuint32_t box[2] = {kFKC, (cuuint32_t)C};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(weight), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level weight) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
+  }
+  const int smem = (int)FuseTmaSmem<C>::kTotal;
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  int dev = 0, sms = 0;
+  SPEI_CUDA(cudaGetDevice(&dev));
+  SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTmaSmem<C>::kCtasPerSm;
+  fuse_level_tma_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), kFTmaThreads, smem, st>>>(tmd, tmt, tmw, dec, S, weight, bias, out, n, h, w, scale);
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
+}
+
+template <int C>
+static int launch_fuse_tc_t(int n, int h, int w, int scale, const float* dec, const float* t, const float* S, const float* weight,
+                            const float* bias, float* out, cudaStream_t st) {
+  const size_t plane = (size_t)h * scale * w * scale;
+  const int smem = (int)FuseTcSmem<C>::kTotal;
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tc_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  int dev = 0, sms = 0;
+  SPEI_CUDA(cudaGetDevice(&dev));
+  SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * (C == 128 ? 2 : 3);
+  fuse_level_tc_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), kFThreads, smem, st>>>(dec, t, S, weight, bias, out, n, h, w, scale);
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
+}
+
+int launch_fuse_level_tc(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
+                         const float* weight, const float* bias, float* out, cudaStream_t st) {
+  if (n > 65535) { set_error("fuse_level: n too large"); return SPEI_ERR_ARG; }
+  const size_t plane = (size_t)h * scale * w * scale;
+  static const bool no_tma = getenv("SPEI_FUSE_NO_TMA") != nullptr;  // A/B switch
+  if (!no_tma && plane % 4 == 0 && (long long)n * c < (1ll << 31) && plane < (1ull << 31)) {  // TMA needs 16-byte plane strides
+    if (c == 128) return launch_fuse_tma_t<128>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+    if (c == 64) return launch_fuse_tma_t<64>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+    if (c == 32) return launch_fuse_tma_t<32>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  }
+  if (c == 128) return launch_fuse_tc_t<128>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  if (c == 64) return launch_fuse_tc_t<64>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  if (c == 32) return launch_fuse_tc_t<32>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  set_error("fuse_level: unsupported channel count %d", c);
+  return SPEI_ERR_ARG;
+}
+
+}  // namespace spei

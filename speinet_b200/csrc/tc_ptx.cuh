@@ -31,6 +31,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Pure polling wait (mbarrier.test_wait never suspends the thread): for fine-grained producer/consumer hand-offs
+// where the wake-up latency of a suspended try_wait would dominate the stage time.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int* error_flag) {
+  uint32_t ok = 0, spins = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xfffu) == 0) {
+      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
+      if (clock64() - t0 > 4000000000ll) {
+        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
+        return;
+      }
+    }
+  }
+}
 // try_wait with a suspend-time hint (ns): the waiting warp is parked by the hardware instead of burning
 // issue slots that the epilogue warps of the same SM sub-partition need
 __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
@@ -85,6 +110,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       }
     }
   }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
