@@ -30,6 +30,7 @@
 //   warps 4-11 epilogue, two groups of four (warp % 4 = the tile row v it owns): group h handles key rows
 //             [h*ceil(Ny/2), ...) of every tile and keeps its own top-k list per query (the rescoring merges lists)
 #include <cuda.h>
+#include <cstdio>
 
 #include "spei_common.cuh"
 #include "tc_ptx.cuh"
@@ -46,7 +47,8 @@ constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       //
 constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
 constexpr uint32_t kSNumBars = 2 * kStages + 6;
 constexpr uint32_t kSRkOffset = kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
-constexpr uint32_t kSSmemBytes = kSRkOffset + 8 * 128 * 4;
+constexpr uint32_t kSRkWarpFloats = 132;  // [<=4 rows][32] reciprocal key norms + 4 row maxima
+constexpr uint32_t kSSmemBytes = kSRkOffset + 8 * kSRkWarpFloats * 4;
 static_assert(kSRkOffset % 16 == 0, "key-norm staging must be float4 aligned");
 constexpr uint32_t kSTmemCols = 512;
 constexpr uint32_t kSAccCols = 256;
@@ -55,7 +57,7 @@ struct TcsParams {
   int n, rf, QT, KT, G, maxseg;
   long long P;
   int q_tu, q_orient, Uq, Vq, W, L;
-  int k_tu, k_tiles_img, k_orient, Ny, Wr, lk1, UkP, VkT;
+  int k_tu, k_tvn, k_tiles_img, k_orient, Ny, Wr, lk1, UkP, VkT;
   uint32_t idesc, stage_bytes, k_lbo;
   float win;
   const float* rq;
@@ -66,6 +68,23 @@ struct TcsParams {
   int* error_flag;
 };
 
+// (reference frame, tile row, tile column) of key tile kt, kept incrementally: the per-tile integer divisions were
+// ~15 % of the epilogue warps' instructions (ncu source view, round 1)
+struct KeyTile { int f, tv, tu; };
+__device__ __forceinline__ KeyTile key_tile_decode(int kt, int tiles_img, int k_tu) {
+  KeyTile t;
+  t.f = kt / tiles_img;
+  const int kti = kt - t.f * tiles_img;
+  t.tv = kti / k_tu;
+  t.tu = kti - t.tv * k_tu;
+  return t;
+}
+__device__ __forceinline__ KeyTile key_tile_next(KeyTile t, int k_tu, int k_tvn, int rf) {  // mirrors next_pair's kt + 1 (wraps to 0)
+  if (++t.tu == k_tu) { t.tu = 0; if (++t.tv == k_tvn) { t.tv = 0; if (++t.f == rf) t.f = 0; } }
+  return t;
+}
+
+template <bool kDebug>
 __global__ void __launch_bounds__(kSThreads, 1)
 relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const TcsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -104,7 +123,8 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       uint32_t stage = 0, phase = 0;
       int qloaded = 0;
       PairIdx ix = decode_pair(pb, p.QT, p.KT);
-      for (long long pp = pb; pp < pe; ++pp, ix = next_pair(ix, p.QT, p.KT)) {
+      KeyTile kc = key_tile_decode(ix.kt, p.k_tiles_img, p.k_tu);
+      for (long long pp = pb; pp < pe; ++pp, ix = next_pair(ix, p.QT, p.KT), kc = key_tile_next(kc, p.k_tu, p.k_tvn, p.rf)) {
         if (pp == pb || ix.kt == 0) {
           if (qloaded > 0) mbar_wait(bar_qfree, (uint32_t)((qloaded - 1) & 1), p.error_flag);
           const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
@@ -114,8 +134,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           tma_load_4d(sQ, &tmq, bar_qfull, qtu * kSTileU * 8, qtv * kSQTileV, 0, ix.item);
           ++qloaded;
         }
-        const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
-        const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
+        const int f = kc.f, ktv = kc.tv, ktu = kc.tu;
         for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
           mbar_wait_parked(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
           mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes);
@@ -132,17 +151,23 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       int qused = 0;
       uint32_t tile_i = 0;
       PairIdx ix = decode_pair(pb, p.QT, p.KT);
+#ifdef SPEI_TCS_PROF
+      long long pt0 = clock64(), p_tempty = 0, p_full = 0;
+#define PROF_T(acc_, stmt) { const long long c0_ = clock64(); stmt; acc_ += clock64() - c0_; }
+#else
+#define PROF_T(acc_, stmt) { stmt; }
+#endif
       for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
         if (pp == pb || ix.kt == 0) {
           mbar_wait(bar_qfull, (uint32_t)(qused & 1), p.error_flag);
           ++qused;
         }
         const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
-        mbar_wait_parked(bar_tempty + 8 * acc, (use & 1u) ^ 1u, p.error_flag);
+        PROF_T(p_tempty, mbar_wait_parked(bar_tempty + 8 * acc, (use & 1u) ^ 1u, p.error_flag));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kSAccCols;
         for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
-          mbar_wait_parked(bar_full + 8 * stage, phase, p.error_flag);
+          PROF_T(p_full, mbar_wait_parked(bar_full + 8 * stage, phase, p.error_flag));
           tc_fence_after();
           const uint32_t kbase = sK + stage * kSStageBytesMax;
 #pragma unroll
@@ -162,6 +187,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         tc_commit(bar_tfull + 8 * acc);
         if (ix.kt == p.KT - 1 && pp + 1 < pe) tc_commit(bar_qfree);
       }
+#ifdef SPEI_TCS_PROF
+      if (b == 3) printf("mma: total %lld wait_tempty %lld wait_full %lld tiles %lld\n", clock64() - pt0, p_tempty, p_full, pe - pb);
+#endif
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
@@ -175,12 +203,10 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     uint32_t tile_i = 0;
     long long qlin = -1;
     float winq = 0.f;
-    float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * 128;  // this warp's key norms: [<=4 rows][32]
+    float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * kSRkWarpFloats;  // this warp's key norms: [<=4 rows][32]
     // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=4 rows][32] reciprocal norms
-    auto rk_prefetch = [&](const PairIdx ix, float2 (&pre)[2]) {
-      const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
-      const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
-      const float* base = p.rkpad + ((size_t)(ix.item * p.rf + f) * p.VkT + ktv * p.Ny + r_lo) * p.UkP + ktu * kSTileU;
+    auto rk_prefetch = [&](int item, const KeyTile kt, float2 (&pre)[2]) {
+      const float* base = p.rkpad + ((size_t)(item * p.rf + kt.f) * p.VkT + kt.tv * p.Ny + r_lo) * p.UkP + kt.tu * kSTileU;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int e2 = lane + 32 * j, row = e2 >> 4;
@@ -190,8 +216,12 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     };
     float2 pre[2];
     PairIdx ix = decode_pair(pb, p.QT, p.KT);
-    if (pb < pe) rk_prefetch(ix, pre);
-    for (long long pp = pb; pp < pe; ++pp, ++tile_i, ix = next_pair(ix, p.QT, p.KT)) {
+    KeyTile kc = key_tile_decode(ix.kt, p.k_tiles_img, p.k_tu);
+    if (pb < pe) rk_prefetch(ix.item, kc, pre);
+#ifdef SPEI_TCS_PROF
+    long long et0 = clock64(), e_tfull = 0, e_rows = 0, e_rc0 = 0;
+#endif
+    for (long long pp = pb; pp < pe; ++pp, ++tile_i) {
       if (pp == pb || ix.kt == 0) {
 #pragma unroll
         for (int s = 0; s < kTopK; ++s) { tv[s] = -INFINITY; ti[s] = -1; }
@@ -201,17 +231,30 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         winq = qlin >= 0 ? p.win / __ldg(p.rq + qlin) : 0.f;
       }
       const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
-      const int f = ix.kt / p.k_tiles_img, kti = ix.kt - f * p.k_tiles_img;
-      const int ktv = kti / p.k_tu, ktu = kti - ktv * p.k_tu;
-      const int ku0 = ktu * kSTileU - 1, kv0 = ktv * p.Ny;
+      const int f = kc.f;
+      const int ku0 = kc.tu * kSTileU - 1, kv0 = kc.tv * p.Ny;
+      // largest reciprocal norm of every key row (NaN = keys outside the image are ignored by fmaxf): the row test
+      // below bounds all 30 scores of a row by (largest tap sum) x (largest reciprocal norm)
+      float rmax0 = fmaxf(pre[0].x, pre[0].y), rmax1 = fmaxf(pre[1].x, pre[1].y);
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        rmax0 = fmaxf(rmax0, __shfl_xor_sync(0xffffffffu, rmax0, o));
+        rmax1 = fmaxf(rmax1, __shfl_xor_sync(0xffffffffu, rmax1, o));
+      }
       __syncwarp();
       reinterpret_cast<float2*>(rk_s)[lane] = pre[0];
       reinterpret_cast<float2*>(rk_s)[lane + 32] = pre[1];
+      if ((lane & 15) == 0) { rk_s[128 + (lane >> 4)] = rmax0; rk_s[130 + (lane >> 4)] = rmax1; }
       __syncwarp();
-      if (pp + 1 < pe) rk_prefetch(next_pair(ix, p.QT, p.KT), pre);
-      mbar_wait_parked(bar_tfull + 8 * acc, use & 1u, p.error_flag);
+      const PairIdx nx = next_pair(ix, p.QT, p.KT);
+      const KeyTile kn = key_tile_next(kc, p.k_tu, p.k_tvn, p.rf);
+      if (pp + 1 < pe) rk_prefetch(nx.item, kn, pre);
+      PROF_T(e_tfull, mbar_wait_parked(bar_tfull + 8 * acc, use & 1u, p.error_flag));
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * kSAccCols + ((uint32_t)(ew * 32) << 16);
+#ifdef SPEI_TCS_PROF
+      e_rc0 = clock64();
+#endif
 
       // One key row (32 accumulator columns = two TMEM loads) per iteration.
       uint32_t a[16], c[16];
@@ -219,10 +262,19 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         tc_ld16(taddr + r_lo * 32, a);
         tc_ld16(taddr + r_lo * 32 + 16, c);
       }
+#ifdef SPEI_TCS_NOEPI     // timing experiment only: the MMA / TMA pipeline without any epilogue work
+      tc_wait_ld();
+      if (false)
+#endif
 #pragma unroll 1
       for (int r = r_lo; r < r_hi; ++r) {
         tc_wait_ld();
-        if (p.debug_acc && pp == 0) {
+#ifdef SPEI_TCS_LDONLY   // timing experiment only: TMEM loads without any arithmetic
+        if (r + 1 < r_hi) { tc_ld16(taddr + (r + 1) * 32, a); tc_ld16(taddr + (r + 1) * 32 + 16, c); }
+        if (a[0] == 0x7fc12345u && c[3] == 0x7fc12345u) tv[0] = 1.f;
+        continue;
+#endif
+        if (kDebug && p.debug_acc && pp == 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             p.debug_acc[(size_t)m * kSAccCols + r * 32 + i] = __uint_as_float(a[i]);
@@ -239,8 +291,13 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           up[0] = 0.f; dn[0] = 0.f; up[31] = 0.f; dn[31] = 0.f;
 #pragma unroll
           for (int i = 1; i < 31; ++i) {
+#ifdef SPEI_TCS_NOSHFL   // timing experiment only (wrong sums): what the lane exchange costs
+            up[i] = x[i - 1];
+            dn[i] = x[i + 1];
+#else
             up[i] = __shfl_up_sync(0xffffffffu, x[i - 1], 1);
             dn[i] = __shfl_down_sync(0xffffffffu, x[i + 1], 1);
+#endif
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -249,24 +306,37 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
             fadd2(s[i], s[i + 1], t0, t1, x[i], x[i + 1]);
           }
         }
-        if (r + 1 < r_hi) {  // a[], c[] are consumed: refill while the scores are examined
+#ifndef SPEI_TCS_NOLD      // (timing experiment: arithmetic without the TMEM reloads)
+        if (r + 1 < r_hi)
+#else
+        if (false)
+#endif
+        {  // a[], c[] are consumed: refill while the scores are examined
           tc_ld16(taddr + (r + 1) * 32, a);
           tc_ld16(taddr + (r + 1) * 32 + 16, c);
         }
-        float v[32];
-        const float* rkr = rk_s + (r - r_lo) * 32;
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 t4 = reinterpret_cast<const float4*>(rkr)[i4];  // broadcast reads
-          fmul2(v[4 * i4], v[4 * i4 + 1], s[4 * i4], s[4 * i4 + 1], t4.x, t4.y);  // NaN for keys outside the image
-          fmul2(v[4 * i4 + 2], v[4 * i4 + 3], s[4 * i4 + 2], s[4 * i4 + 3], t4.z, t4.w);
+        // Row test on the un-normalised tap sums: score[i] = s[i] * rk[i] <= max(s) * max(rk) when max(s) > 0 and
+        // <= 0 otherwise (rk > 0), so a row whose bound does not beat the entry bar holds no candidate and its key
+        // norms are never read (one broadcast LDS + 16 FMNMX instead of 8 LDS.128 + 16 FMUL2 + 16 FMNMX per row).
+        float smax;
+        {
+          const float m0 = fmax3(s[1], s[2], s[3]), m1 = fmax3(s[4], s[5], s[6]), m2 = fmax3(s[7], s[8], s[9]);
+          const float m3 = fmax3(s[10], s[11], s[12]), m4 = fmax3(s[13], s[14], s[15]), m5 = fmax3(s[16], s[17], s[18]);
+          const float m6 = fmax3(s[19], s[20], s[21]), m7 = fmax3(s[22], s[23], s[24]), m8 = fmax3(s[25], s[26], s[27]);
+          const float m9 = fmax3(s[28], s[29], s[30]);
+          smax = fmaxf(fmax3(fmax3(m0, m1, m2), fmax3(m3, m4, m5), fmax3(m6, m7, m8)), m9);
         }
-        float mxa = fmaxf(fmaxf(fmaxf(v[1], v[2]), fmaxf(v[3], v[4])), fmaxf(fmaxf(v[5], v[6]), fmaxf(v[7], v[8])));
-        mxa = fmaxf(mxa, fmaxf(fmaxf(fmaxf(v[9], v[10]), fmaxf(v[11], v[12])), fmaxf(fmaxf(v[13], v[14]), v[15])));
-        float mxc = fmaxf(fmaxf(fmaxf(v[16], v[17]), fmaxf(v[18], v[19])), fmaxf(fmaxf(v[20], v[21]), fmaxf(v[22], v[23])));
-        mxc = fmaxf(mxc, fmaxf(fmaxf(fmaxf(v[24], v[25]), fmaxf(v[26], v[27])), fmaxf(fmaxf(v[28], v[29]), v[30])));
         const float thr = fmaxf(tv[kTopK - 1], tv[0] - winq);
-        if (qlin >= 0 && fmaxf(mxa, mxc) > thr) {
+        const float bound = smax > 0.f ? smax * rk_s[128 + (r - r_lo)] : 0.f;   // NaN (no key of the row in the image) fails the test
+        if (qlin >= 0 && bound > thr) {
+          float v[32];
+          const float* rkr = rk_s + (r - r_lo) * 32;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 t4 = reinterpret_cast<const float4*>(rkr)[i4];  // broadcast reads
+            fmul2(v[4 * i4], v[4 * i4 + 1], s[4 * i4], s[4 * i4 + 1], t4.x, t4.y);  // NaN for keys outside the image
+            fmul2(v[4 * i4 + 2], v[4 * i4 + 3], s[4 * i4 + 2], s[4 * i4 + 3], t4.z, t4.w);
+          }
           // compact slow path: bit mask of the qualifying columns (halo columns 0 / 31 excluded), then one sorted
           // insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
           unsigned msk = 0;
@@ -299,6 +369,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           }
         }
       }
+#ifdef SPEI_TCS_PROF
+      e_rows += clock64() - e_rc0;
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -315,7 +388,12 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           }
         }
       }
+      ix = nx;
+      kc = kn;
     }
+#ifdef SPEI_TCS_PROF
+    if (b == 3 && lane == 0) printf("epi warp %d: total %lld wait_tfull %lld rows %lld\n", warp, clock64() - et0, e_tfull, e_rows);
+#endif
   }
 
   tc_fence_before();
@@ -352,7 +430,7 @@ int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   TcsParams t{};
   t.n = p.n; t.rf = p.rf; t.QT = p.QT; t.KT = p.KT; t.G = p.G; t.maxseg = p.maxseg; t.P = p.P;
   t.q_tu = p.q.tu; t.q_orient = p.q.orient; t.Uq = p.q.U; t.Vq = p.q.V; t.W = p.W; t.L = p.H * p.W;
-  t.k_tu = p.k.tu; t.k_tiles_img = p.k.tiles(); t.k_orient = p.k.orient; t.Ny = p.k.tile_v; t.Wr = p.Wr; t.lk1 = p.Hr * p.Wr;
+  t.k_tu = p.k.tu; t.k_tvn = p.k.tv; t.k_tiles_img = p.k.tiles(); t.k_orient = p.k.orient; t.Ny = p.k.tile_v; t.Wr = p.Wr; t.lk1 = p.Hr * p.Wr;
   t.UkP = p.k.Upad; t.VkT = p.k.tv * p.k.tile_v;
   const uint32_t ncols = (uint32_t)(kSBoxU * p.k.tile_v);
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bits 17-22, M>>4 at bits 24-28
@@ -367,10 +445,10 @@ int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   t.debug_acc = take_debug_acc();
   t.error_flag = (int*)(ws + p.off_errflag);
   SPEI_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int), st));
-  SPEI_CUDA(cudaFuncSetAttribute(relevance_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes));
-  SPEI_CUDA(cudaFuncSetAttribute(relevance_tcs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 (int)cudaSharedmemCarveoutMaxShared));
-  relevance_tcs_kernel<<<p.G, kSThreads, kSSmemBytes, st>>>(tmq, tmk, t);
+  auto kern = t.debug_acc ? relevance_tcs_kernel<true> : relevance_tcs_kernel<false>;
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes));
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  kern<<<p.G, kSThreads, kSSmemBytes, st>>>(tmq, tmk, t);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }

@@ -94,6 +94,7 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float a0, float a1, 
   asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}"
       : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3 on sm_100
 // Bounded wait: a protocol bug must surface as an error code, not as a hung GPU.  On a ~2 s timeout the
 // waiter records which barrier starved in *error_flag; from then on every wait in the grid returns
 // immediately, so the kernel drains (with garbage results) and the host can read the code back.
