@@ -11,6 +11,8 @@
 // The <=9 terms are added in the order of torch's col2im so the result is bit-identical to
 // F.fold: ascending patch origin on CUDA (ATen/native/cuda/im2col.cuh:139-154), ascending (ki,kj)
 // on CPU (ATen/native/im2col.h:131-146); then x*(1/9f) resp. x/9 (hard part 4).
+#include <cstdlib>
+
 #include "spei_common.cuh"
 
 namespace spei {
@@ -38,6 +40,68 @@ __device__ __forceinline__ float2 vzero(float2) { return make_float2(0.f, 0.f); 
 __device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 __device__ const float4 g_zero16 = {0.f, 0.f, 0.f, 0.f};  // source of every non-contributing neighbour
+
+// Channel-slab variant for the finest level (S = 4, 118 MB of reference per 720p item): with a scattered match
+// field every reference pixel is covered by ~9 different gathered patches at unrelated times, and the whole level
+// does not stay in L2, so the kernel above re-reads it ~9x from DRAM (ncu: 1.19 GB per launch).  Here the
+// slowest grid dimension is an 8-channel slab (29.5 MB at 720p, L2 resident while every query cell is processed
+// for it), so DRAM sees each slab once; one block handles the S sub-rows of a cell row so the index decode is
+// still shared by S x 8 x 32 outputs.  Same adds in the same order: bit-identical to the kernel above.
+// grid: (ceil(W/32), H, n * C/8)   block: (32 cells, 8 channels)
+template <int S, bool kCpuOrder, bool kTrueDiv>
+__global__ void __launch_bounds__(256)
+gather_fold_slab_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
+                        int H, int W, int Hr, int Wr) {
+  using V = typename Vec<S>::T;
+  __shared__ long long s_off[9][32];  // per (neighbour, cell): float offset of the source run of sub-row 0, -1 = none
+  const int X0 = blockIdx.x * 32, X = X0 + threadIdx.x;
+  const int Y = blockIdx.y;
+  const int slabs = C / 8, n = blockIdx.z / slabs, c = (blockIdx.z - n * slabs) * 8 + threadIdx.y;
+  const int lk1 = Hr * Wr, jmax = rf * lk1 - 1;
+  const size_t ref_plane = (size_t)(S * Hr) * (S * Wr);
+  const int ref_pitch = S * Wr;
+  const int32_t* a = arg + (size_t)n * H * W;
+  for (int e = threadIdx.y * 32 + threadIdx.x; e < 9 * 32; e += 256) {
+    const int t = e >> 5, cell = e & 31;
+    const int tt = kCpuOrder ? 8 - t : t;
+    const int dy = tt / 3 - 1, dx = tt % 3 - 1;
+    const int Xc = X0 + cell, qy = Y + dy, qx = Xc + dx;
+    long long o = -1;
+    if (Xc < W && qy >= 0 && qy < H && qx >= 0 && qx < W) {
+      int j = __ldg(a + qy * W + qx);
+      j = min(max(j, 0), jmax);
+      const int f = j / lk1, rem = j - f * lk1;
+      const int hr = rem / Wr, wr = rem - hr * Wr;
+      const int cy = Y + hr - qy, cx = Xc + wr - qx;  // source cell
+      if (cy >= 0 && cy < Hr && cx >= 0 && cx < Wr)
+        o = (long long)f * C * (long long)ref_plane + (long long)(cy * S) * ref_pitch + (long long)cx * S;
+    }
+    s_off[t][cell] = o;
+  }
+  __syncthreads();
+  if (X >= W) return;
+  const float* rbase = ref + (size_t)n * rf * C * ref_plane + (size_t)c * ref_plane;
+  const float* base[9];
+  unsigned step[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const long long o = s_off[t][threadIdx.x];
+    base[t] = o >= 0 ? rbase + o : reinterpret_cast<const float*>(&g_zero16);
+    step[t] = o >= 0 ? (unsigned)ref_pitch : 0u;   // sub-row stride (0 for the zero constant)
+  }
+  const size_t out_plane = (size_t)(S * H) * (S * W);
+  float* obase = out + ((size_t)n * C + c) * out_plane + (size_t)(Y * S) * (S * W) + (size_t)X * S;
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    V v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = __ldg(reinterpret_cast<const V*>(base[t] + (size_t)r * step[t]));
+    V acc = vzero(V{});
+#pragma unroll
+    for (int t = 0; t < 9; ++t) vadd(acc, v[t]);
+    __stcs(reinterpret_cast<V*>(obase + (size_t)r * (S * W)), fin<kTrueDiv>(acc));
+  }
+}
 
 // grid: (ceil(W/32), S*H, n)   block: (32 cells, 8 channel lanes)
 template <int S, bool kCpuOrder, bool kTrueDiv>
@@ -116,7 +180,15 @@ int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int s
     else { if (true_div) GF(S_, false, true); else GF(S_, false, false); }          \
   } while (0)
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
-  if (scale == 1) GFS(1);
+  static const bool no_slab = getenv("SPEI_GATHER_NO_SLAB") != nullptr;  // A/B switch
+  if (scale == 4 && !no_slab && (long long)n * (c / 8) <= 65535) {
+    const dim3 sgrid((w + 31) / 32, h, n * (c / 8));
+#define GFL(O_, D_) gather_fold_slab_kernel<4, O_, D_><<<sgrid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
+    if (cpu_order) { if (true_div) GFL(true, true); else GFL(true, false); }
+    else { if (true_div) GFL(false, true); else GFL(false, false); }
+#undef GFL
+  }
+  else if (scale == 1) GFS(1);
   else if (scale == 2) GFS(2);
   else GFS(4);
 #undef GFS

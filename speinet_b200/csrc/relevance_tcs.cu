@@ -202,7 +202,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     int ti[kTopK];
     uint32_t tile_i = 0;
     long long qlin = -1;
-    float winq = 0.f;
+    float winq = 0.f, floor0 = -INFINITY;
     float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * kSRkWarpFloats;  // this warp's key norms: [<=4 rows][32]
     // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=4 rows][32] reciprocal norms
     auto rk_prefetch = [&](int item, const KeyTile kt, float2 (&pre)[2]) {
@@ -212,6 +212,30 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         const int e2 = lane + 32 * j, row = e2 >> 4;
         pre[j] = (r_lo + row) < r_hi ? __ldg(reinterpret_cast<const float2*>(base + (size_t)row * p.UkP) + (e2 & 15))
                                      : make_float2(0.f, 0.f);
+      }
+    };
+    // tap sums of one key row from the two TMEM loads: (m-1, col-1) + (m, col) + (m+1, col+1).  Columns 0 and 31 are
+    // halo (their sums are computed on garbage neighbours and never looked at); packed f32x2 adds.
+    auto tap_sums = [&](const uint32_t (&a)[16], const uint32_t (&c)[16], float (&s)[32]) {
+      float x[32], up[32], dn[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { x[i] = __uint_as_float(a[i]); x[16 + i] = __uint_as_float(c[i]); }
+      up[0] = 0.f; dn[0] = 0.f; up[31] = 0.f; dn[31] = 0.f;
+#pragma unroll
+      for (int i = 1; i < 31; ++i) {
+#ifdef SPEI_TCS_NOSHFL   // timing experiment only (wrong sums): what the lane exchange costs
+        up[i] = x[i - 1];
+        dn[i] = x[i + 1];
+#else
+        up[i] = __shfl_up_sync(0xffffffffu, x[i - 1], 1);
+        dn[i] = __shfl_down_sync(0xffffffffu, x[i + 1], 1);
+#endif
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float t0, t1;
+        fadd2(t0, t1, up[i], up[i + 1], dn[i], dn[i + 1]);
+        fadd2(s[i], s[i + 1], t0, t1, x[i], x[i + 1]);
       }
     };
     float2 pre[2];
@@ -229,7 +253,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         const int u = qtu * kSTileU + qu - 1, v = qtv * kSQTileV + qv;
         qlin = (qu >= 1 && qu <= kSTileU && u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
         winq = qlin >= 0 ? p.win / __ldg(p.rq + qlin) : 0.f;
+        floor0 = -INFINITY;
       }
+      const bool fresh = pp == pb || ix.kt == 0;   // first tile of a (query tile, key segment)
       const uint32_t acc = tile_i & 1u, use = tile_i >> 1;
       const int f = kc.f;
       const int ku0 = kc.tu * kSTileU - 1, kv0 = kc.tv * p.Ny;
@@ -262,6 +288,35 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         tc_ld16(taddr + r_lo * 32, a);
         tc_ld16(taddr + r_lo * 32 + 16, c);
       }
+      if (fresh && r_lo < r_hi) {
+        // First tile of a list: one extra sweep over this group's rows finds their best score, and the entry bar
+        // starts at (that - window) instead of -inf.  Without it the first rows push every key through the sorted
+        // insertion (the lists restart for every query tile: that transient was ~15 % of the epilogue instructions).
+        float best0 = -INFINITY;
+#pragma unroll 1
+        for (int r = r_lo; r < r_hi; ++r) {
+          tc_wait_ld();
+          float s[32];
+          tap_sums(a, c, s);
+          const int rn = r + 1 < r_hi ? r + 1 : r_lo;   // the last refill re-reads the first row for the main sweep
+          tc_ld16(taddr + rn * 32, a);
+          tc_ld16(taddr + rn * 32 + 16, c);
+          const float* rkr = rk_s + (r - r_lo) * 32;
+          float vmax = -INFINITY;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 t4 = reinterpret_cast<const float4*>(rkr)[i4];
+            float v0, v1, v2, v3;
+            fmul2(v0, v1, s[4 * i4], s[4 * i4 + 1], t4.x, t4.y);
+            fmul2(v2, v3, s[4 * i4 + 2], s[4 * i4 + 3], t4.z, t4.w);
+            if (i4 == 0) v0 = -INFINITY;     // halo column 0
+            if (i4 == 7) v3 = -INFINITY;     // halo column 31
+            vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));   // fmaxf drops NaN (keys outside the image)
+          }
+          best0 = fmaxf(best0, vmax);
+        }
+        floor0 = best0 - winq;
+      }
 #ifdef SPEI_TCS_NOEPI     // timing experiment only: the MMA / TMA pipeline without any epilogue work
       tc_wait_ld();
       if (false)
@@ -281,31 +336,8 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
             p.debug_acc[(size_t)m * kSAccCols + r * 32 + 16 + i] = __uint_as_float(c[i]);
           }
         }
-        // sum of the three u taps: (m-1, col-1) + (m, col) + (m+1, col+1).  Columns 0 and 31 are halo (their sums
-        // are computed on garbage neighbours and never looked at); packed f32x2 adds on the load's register pairs.
         float s[32];
-        {
-          float x[32], up[32], dn[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { x[i] = __uint_as_float(a[i]); x[16 + i] = __uint_as_float(c[i]); }
-          up[0] = 0.f; dn[0] = 0.f; up[31] = 0.f; dn[31] = 0.f;
-#pragma unroll
-          for (int i = 1; i < 31; ++i) {
-#ifdef SPEI_TCS_NOSHFL   // timing experiment only (wrong sums): what the lane exchange costs
-            up[i] = x[i - 1];
-            dn[i] = x[i + 1];
-#else
-            up[i] = __shfl_up_sync(0xffffffffu, x[i - 1], 1);
-            dn[i] = __shfl_down_sync(0xffffffffu, x[i + 1], 1);
-#endif
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0, t1;
-            fadd2(t0, t1, up[i], up[i + 1], dn[i], dn[i + 1]);
-            fadd2(s[i], s[i + 1], t0, t1, x[i], x[i + 1]);
-          }
-        }
+        tap_sums(a, c, s);
 #ifndef SPEI_TCS_NOLD      // (timing experiment: arithmetic without the TMEM reloads)
         if (r + 1 < r_hi)
 #else
@@ -326,7 +358,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           const float m9 = fmax3(s[28], s[29], s[30]);
           smax = fmaxf(fmax3(fmax3(m0, m1, m2), fmax3(m3, m4, m5), fmax3(m6, m7, m8)), m9);
         }
-        const float thr = fmaxf(tv[kTopK - 1], tv[0] - winq);
+        const float thr = fmax3(tv[kTopK - 1], tv[0] - winq, floor0);
         const float bound = smax > 0.f ? smax * rk_s[128 + (r - r_lo)] : 0.f;   // NaN (no key of the row in the image) fails the test
         if (qlin >= 0 && bound > thr) {
           float v[32];
@@ -356,7 +388,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
 #pragma unroll
             for (int j = 0; j < 2; ++j) s2[j] = (i & 8) ? s4[2 * j + 1] : s4[2 * j];
             float x = (i & 16) ? s2[1] : s2[0];
-            if (x > fmaxf(tv[kTopK - 1], tv[0] - winq)) {
+            if (x > fmax3(tv[kTopK - 1], tv[0] - winq, floor0)) {
               int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku0 + i, kv0 + r, p.Wr);
 #pragma unroll
               for (int s = 0; s < kTopK; ++s) {
