@@ -35,7 +35,7 @@ import torch  # noqa: E402
 H, W, C3 = 180, 320, 128                      # lv3 grid of a 1280x720 frame (speinet.py:124-127)
 L = H * W
 FLOPS_RELEVANCE = 2.0 * L * L * 9 * C3        # 7.644 TFLOP
-KERNELS_PER_STEP = 2 + 3 + 1 + 5 + 4 + 3      # stage q, stage k, tcgen05, rescore group, gather/fold x3 (+ lv2 staging), fuse x3
+KERNELS_PER_STEP = 3 + 4 + 1 + 5 + 4 + 3      # stage q, stage k (incl. padding zero-fill), tcgen05, rescore group, gather/fold x3 (+ lv2 staging), fuse x3
 WORKLOAD = "searchtransfer_fusion_1280x720_1ref"
 
 
@@ -369,15 +369,20 @@ def run_ours(args, rank, world, local_rank):
             dist.all_gather_into_tensor(frame_out, Fo[1][:, :3].contiguous())
         torch.cuda.synchronize(dev)
 
+    e2e_repeats = []
     if args.no_e2e:
         n_e2e, e2e_s, e2e_check = 0, 1.0, None
     else:
         e2e_run(3)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_run(n_e2e)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        # three timed repeats of the same n_e2e clips, median reported: the leg is PCIe bound (650 MB per clip) and one
+        # repeat of ~0.15 s is exposed to host-side hiccups (a 3x slower outlier was seen once in round 1)
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            e2e_run(n_e2e)
+            barrier()
+            e2e_repeats.append(time.perf_counter() - t0)
+        e2e_s = sorted(e2e_repeats)[1]
         e2e_check = float((out_sets[(n_e2e - 1) & 1]["f1"] - Fo[1].cpu()).abs().max())  # same inputs -> same fused features
     clocks = sampler.stop()
 
@@ -416,7 +421,8 @@ def run_ours(args, rank, world, local_rank):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture under profiles/
                      "traffic": 30.87e6 if args.search == "tcs" else 30.6e6, "traffic_source": "profiles/ ncu capture; algorithmic operand bytes 29.5e6"},
         "e2e": {"value": world * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "max_abs_diff_vs_device_path": e2e_check,
+                "steps": n_e2e, "repeats_s": [round(x, 5) for x in e2e_repeats], "timing": "median of 3 repeats (this rank; max over ranks of the medians)",
+                "max_abs_diff_vs_device_path": e2e_check,
                 "api": "speinet_b200.HostPipeline (SearchTransfer + fuse_level), pinned host buffers, H2D+D2H of every clip inside the timed region, 3-stream overlap"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,

@@ -1,4 +1,4 @@
-"""Shared helpers for the GPU parity tests and tools/gpu_diag.py (test infrastructure)."""
+"""Shared helpers for the GPU parity tests and tests/diag/gpu_diag.py (test infrastructure)."""
 from __future__ import annotations
 
 import ctypes

@@ -6,7 +6,7 @@ can handle, captures (f_fusion, sharp_lv3) at speinet.py:135 and emulates the tc
 numpy: operands rounded to bf16, fp32 patch norms, exact accumulation.  Reports, for the default and the
 rigorous window, how many keys fall inside the window of the best bf16 score (= candidates rescored),
 how many queries would saturate a kTopK=8 list (= exhaustive fallback) and the largest bf16 scoring
-error -- the evidence behind `eps` in DESIGN.md section 4(b').   Usage: python tools/analyze_real_features.py [H W]
+error -- the evidence behind `eps` in DESIGN.md section 4(b').   Usage: python tests/diag/analyze_real_features.py [H W]
 """
 import json
 import os
@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import make_golden_model as shim  # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Stage-by-stage GPU diagnostics of the hot path (run on the B200 box; test infrastructure).
 
-    python tools/gpu_diag.py --stage env|fold|exact|tile|tc|fuse|time720 [--out gpurun_out/diag]
+    python tests/diag/gpu_diag.py --stage env|fold|exact|tile|tc|fuse|time720 [--out gpurun_out/diag]
 
 Every stage prints a compact report and appends a JSON record to <out>_<stage>.json, so one
 `gpurun` call tells which layer of the pipeline is wrong.  Uses the oracle only as the checker.
@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -7,7 +7,7 @@ for round in 1 2; do
 for v in $VARS; do
   if [ "$v" = default ]; then unset SPEINET_B200_LIB; else export SPEINET_B200_LIB=$PWD/build_ab/lib_$v.so; fi
   if [ $round = 1 ]; then
-    timeout 300 python tools/gpu_diag.py --stage tc --out gpurun_out/ab_${v} > gpurun_out/ab_${v}_tc.log 2>&1; echo "$v tc exit $?"
+    timeout 300 python tests/diag/gpu_diag.py --stage tc --out gpurun_out/ab_${v} > gpurun_out/ab_${v}_tc.log 2>&1; echo "$v tc exit $?"
     grep -E "^tc " gpurun_out/ab_${v}_tc.log | cut -c 1-260
   fi
   timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/ab_${v}_bench$round.json 2> gpurun_out/ab_${v}_bench$round.err; echo "$v bench exit $?"

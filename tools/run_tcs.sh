@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU check of the tap-sharing search: raw accumulator tile, search parity, robustness, bench A/B vs dense
 mkdir -p gpurun_out
-for s in ${STAGES:-tile_tcs tcs}; do timeout 300 python tools/gpu_diag.py --stage $s > gpurun_out/diag_$s.log 2>&1; echo "stage $s exit $?"; grep -E "^(tcs|tile|robust) " gpurun_out/diag_$s.log | cut -c 1-600; done
+for s in ${STAGES:-tile_tcs tcs}; do timeout 300 python tests/diag/gpu_diag.py --stage $s > gpurun_out/diag_$s.log 2>&1; echo "stage $s exit $?"; grep -E "^(tcs|tile|robust) " gpurun_out/diag_$s.log | cut -c 1-600; done
 for m in tcs tc; do
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --search $m > gpurun_out/bench_$m.json 2> gpurun_out/bench_$m.err; echo "bench $m exit $?"
 python - <<PY
