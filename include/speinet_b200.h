@@ -5,6 +5,7 @@
  *   model/SearchTransfer.py:24-51   SearchTransfer.forward   -> spei_search_transfer
  *   model/SearchTransfer.py:59-72   SelfTransfer search half -> spei_search_transfer with NULL pyramids
  *   model/speinet.py:93-94,96-97,108-109  _decode fusion     -> spei_fuse_level
+ *   model/rcl.py:22-51              r_l_per_channel          -> spei_rl_deconv
  *
  * Conventions
  *   - extern "C", plain pointers + sizes + a CUDA stream handle (void*, a cudaStream_t).  No torch types.
@@ -121,6 +122,19 @@ int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, co
  *   bias [c]; S [n, 1, h, w].  out may alias neither input. */
 int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const float *dec, const float *t,
                     const float *S, const float *weight, const float *bias, float *out, void *stream);
+
+/* ---- next to the path ---- */
+
+/* The Richardson-Lucy edge prior, model/rcl.py:22-51 r_l_per_channel(image_tensor, blur_kernel, num_iterations,
+ * regularization_strength) (call sites speinet.py:81 with 1 iteration, :129 / :141 with 5), all iterations of all
+ * channels in one kernel:
+ *   image       [n, c, h, w] fp32      the frame (channels are processed independently, rcl.py:27-28)
+ *   blur_kernel [ks, ks] fp32 (device) the [1,1,ks,ks] weight of rcl.py:33 (create_blur_kernel: 5x5 box, rcl.py:18-20);
+ *                                      ks in {3, 5, 7}
+ *   out         [n, c, h, w] fp32      must not alias image
+ * NaN -> 0 and negative -> 0 on the correction factor exactly as rcl.py:39-40. */
+int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32_t num_iterations,
+                   float regularization_strength, const float *image, const float *blur_kernel, float *out, void *stream);
 
 /* ---- diagnostics (used by tests and tools; not part of the reference-facing path) ---- */
 

@@ -2,7 +2,8 @@
 
 This package is a plain numpy (and, for the timed CPU baseline, plain torch-CPU)
 restatement of the reference algorithm in /root/reference/model/SearchTransfer.py
-and of the three fusion lines of /root/reference/model/speinet.py::_decode.
+and of the three fusion lines of /root/reference/model/speinet.py::_decode, plus (SURVEY.md
+section 8(f) row 3) the Richardson-Lucy edge prior of /root/reference/model/rcl.py:22-51.
 
 Nothing in the product package `speinet_b200` imports it.  The only allowed
 importers are `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
@@ -20,3 +21,4 @@ from .search_transfer_np import (  # noqa: F401
     closed_form_transfer, near_tie_agreement,
 )
 from .fusion_np import bicubic_upsample, conv1x1, fuse_level  # noqa: F401
+from .rl_deconv_np import create_blur_kernel, r_l_per_channel  # noqa: F401

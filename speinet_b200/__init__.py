@@ -9,6 +9,7 @@ from .search_transfer import SearchTransfer, SelfTransfer, search_transfer  # no
 from .fusion import fuse_level, decode_fused, install  # noqa: F401
 from .sharding import shard_clips, gather_outputs, row_band, search_transfer_rows, gather_rows  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
+from .rl_deconv import create_blur_kernel, r_l_per_channel  # noqa: F401
 
 __all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "decode_fused", "install",
-           "shard_clips", "gather_outputs", "HostPipeline", "load_library", "LIB_PATH"]
+           "shard_clips", "gather_outputs", "HostPipeline", "create_blur_kernel", "r_l_per_channel", "load_library", "LIB_PATH"]

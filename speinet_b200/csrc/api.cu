@@ -324,6 +324,17 @@ int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, c
   return launch_fuse_level(n, c, h, w, scale, dec, t, S, weight, bias, out, (cudaStream_t)stream);
 }
 
+int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32_t num_iterations, float regularization_strength,
+                   const float* image, const float* blur_kernel, float* out, void* stream) {
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  if (n < 1 || c < 1 || h < 1 || w < 1) { set_error("bad rl_deconv dims n=%d c=%d h=%d w=%d", n, c, h, w); return SPEI_ERR_ARG; }
+  if ((rc = check_ptr(image, "image", 4)) || (rc = check_ptr(blur_kernel, "blur_kernel", 4)) || (rc = check_ptr(out, "out", 4))) return rc;
+  if (out == image) { set_error("rl_deconv: out must not alias image"); return SPEI_ERR_ARG; }
+  return launch_rl_deconv(n, c, h, w, ks, num_iterations, regularization_strength, image, blur_kernel, out, (cudaStream_t)stream);
+}
+
 int spei_search_transfer(const SpeiShape* shape, const float* q, const float* k, const float* ref1, const float* ref2,
                          const float* ref3, float* S, float* T3, float* T2, float* T1, int64_t* arg, int32_t* stats,
                          void* workspace, size_t workspace_bytes, void* stream) {

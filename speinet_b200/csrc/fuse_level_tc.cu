@@ -364,10 +364,15 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
         float x[kFKC];
 #pragma unroll
         for (int c = 0; c < kFKC; ++c) x[c] = rbox[c * kFM + px];
+        // weight row px of this stage: 4 x 16 B at a 64-byte thread stride.  Read in the fixed order j the 8 threads
+        // of a 128-bit shared-memory phase hit only two 4-bank groups (4-way conflict; ncu: 45 % of the kernel's LSU
+        // wavefronts were conflicts), so thread px starts at chunk (px >> 1) & 3 and wraps: all 8 groups distinct.
+        // The chunk index only enters address arithmetic (load here, store below), never a register index.
+        const int jrot = (px >> 1) & 3;
         float4 wv[kFKC / 4];
 #pragma unroll
         for (int j = 0; j < kFKC / 4; ++j)
-          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[(j + jrot) & 3] : make_float4(0.f, 0.f, 0.f, 0.f);
         // generic-proxy reads must be ordered before the async-proxy (TMA) refill of this box: without this
         // fence the refill raced with the reads (measured: sporadic wrong tiles at C = 128, where the ring wraps)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -385,8 +390,9 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
           if (wrow) {
             const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
             ft_split4(w4, hi, lo);
-            st_shared_v4(b_hi + j * L::kBLBO + px * 16, hi);
-            st_shared_v4(b_lo + j * L::kBLBO + px * 16, lo);
+            const uint32_t jj = (uint32_t)((j + jrot) & 3);
+            st_shared_v4(b_hi + jj * L::kBLBO + px * 16, hi);
+            st_shared_v4(b_lo + jj * L::kBLBO + px * 16, lo);
           }
         }
 #else

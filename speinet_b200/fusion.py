@@ -67,8 +67,12 @@ def decode_fused(net, f_fusion, weight_S, sharp_lv3, sharp_lv2, sharp_lv1):
     return rn.outBlock(f_lv1)                                                                           # :120
 
 
-def install(net, fuse: bool = True, **search_kwargs):
+def install(net, fuse: bool = True, edge_prior: bool = True, **search_kwargs):
     """Swap the B200 hot path into a reference-style SPEINet instance (speinet.py:53-54,92).
+
+    With `edge_prior`, the module that defines the network class gets its global `r_l_per_channel`
+    (pulled in by `from model.rcl import *`, speinet.py:8; used at :81, :129, :141) rebound to
+    `speinet_b200.r_l_per_channel`: same signature, one kernel launch instead of ~8 per channel and iteration.
 
     `net.SearchTransfer` / `net.SelfTransfer` are replaced by the modules of this package (weights of
     their unused/used 1x1 convs are carried over, so a strict checkpoint load done before or after
@@ -83,4 +87,10 @@ def install(net, fuse: bool = True, **search_kwargs):
         net.SelfTransfer = new_self
     if fuse:
         net._decode = types.MethodType(decode_fused, net)
+    if edge_prior:
+        import sys
+        from .rl_deconv import r_l_per_channel
+        mod = sys.modules.get(type(net).__module__)
+        if mod is not None and hasattr(mod, "r_l_per_channel"):
+            mod.r_l_per_channel = r_l_per_channel
     return net

@@ -26,7 +26,7 @@ def declared_symbols():
 def test_header_declares_the_path():
     syms = declared_symbols()
     for must in ("spei_search_transfer", "spei_stage_norm", "spei_relevance_argmax", "spei_gather_fold",
-                 "spei_fuse_level", "spei_workspace_bytes", "spei_last_error", "spei_version"):
+                 "spei_fuse_level", "spei_rl_deconv", "spei_workspace_bytes", "spei_last_error", "spei_version"):
         assert must in syms
 
 

@@ -308,6 +308,62 @@ def test_fusion_odd_sizes_vs_oracle():
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
 
 
+# ------------------------------------------------------------------ (f-3) Richardson-Lucy edge prior
+@pytest.mark.parametrize("name", ["uni", "img"])
+@pytest.mark.parametrize("iters", [1, 5])
+def test_rl_deconv_matches_reference_golden(golden, name, iters):
+    g = golden("rl_deconv")
+    got = speinet_b200.r_l_per_channel(cu(g[name]), cu(g["blur_kernel"]), iters, 0.01).cpu().numpy()
+    want = g[f"{name}_it{iters}"]
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)   # reference r_l_per_channel (rcl.py:22-51), CPU fp32
+
+
+def test_rl_deconv_vs_oracle_ragged_tiles_and_kernel_sizes():
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 45, 131)).astype(np.float32)           # not a multiple of the 64 x 32 tile
+    x[0, 0, 5:20, 60:90] = 0.0
+    for ks, iters in ((5, 5), (5, 2), (3, 4), (7, 2)):
+        k = rng.random((1, 1, ks, ks)).astype(np.float32)
+        k /= k.sum()
+        got = speinet_b200.r_l_per_channel(cu(x), cu(k), iters, 0.02).cpu().numpy()
+        want = oracle.r_l_per_channel(x, k, iters, 0.02)
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-4, atol=1e-5)
+
+
+def test_rl_deconv_720p_matches_torch_ops_and_is_one_launch():
+    """Full 1280x720 frame, 5 iterations (speinet.py:129): against the reference's op sequence run with torch on the same
+    GPU (TF32 off so the convolutions are fp32), and channel / batch independence as a size-independent property."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    x = torch.rand(1, 3, 720, 1280, device="cuda")
+    k = speinet_b200.create_blur_kernel().cuda()
+    got = speinet_b200.r_l_per_channel(x, k, 5, 0.01)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        lap = torch.tensor([[0, -1, 0], [-1, 4, -1], [0, -1, 0]], dtype=torch.float32, device="cuda")[None, None]
+        chans = []
+        for c in range(3):
+            xc = x[:, c:c + 1]
+            d = xc.clone()
+            for _ in range(5):
+                cf = xc / F.conv2d(d, k, padding=2)
+                cf[cf != cf] = 0.0
+                cf[cf < 0] = 0.0
+                d = cf * (d + 0.01 * F.conv2d(d, lap, padding=1))
+            chans.append(d)
+        want = torch.cat(chans, dim=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-3)).max().item()
+    assert rel < 1e-4, rel
+    again = speinet_b200.r_l_per_channel(x[:, 1:2].contiguous(), k, 5, 0.01)
+    assert torch.equal(again[:, 0], got[:, 1])
+
+
 # ------------------------------------------------------------------ full size properties --------
 def test_full_size_720p_properties():
     """At BASELINE.json's full size the oracle is too slow; use size-independent properties

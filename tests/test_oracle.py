@@ -144,3 +144,29 @@ def test_torch_port_matches_golden(golden):
     gf = golden("fusion")
     f = fuse_level_torch(t(gf["dec2"]), t(gf["t2"]), t(gf["S"]), t(gf["w2"]), t(gf["b2"]), 2)
     np.testing.assert_allclose(f.numpy(), gf["f2"], rtol=1e-5, atol=1e-6)
+
+
+# ---- Richardson-Lucy edge prior against the reference's own r_l_per_channel ----
+@pytest.mark.parametrize("name", ["uni", "img"])
+@pytest.mark.parametrize("iters", [1, 5])
+def test_rl_deconv_matches_reference(golden, name, iters):
+    g = golden("rl_deconv")
+    got = oracle.r_l_per_channel(g[name], g["blur_kernel"], iters, 0.01)
+    want = g[f"{name}_it{iters}"]
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    # fp32, but torch's CPU convolution associates the 25 taps differently and 5 iterations amplify it: 1e-4 relative
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_rl_deconv_semantics_zero_and_negative():
+    """0/0 -> NaN -> 0 (rcl.py:39), negative correction -> 0 (rcl.py:40), channels independent (rcl.py:27)."""
+    x = np.zeros((1, 2, 9, 11), dtype=np.float32)
+    x[0, 1] = np.linspace(0.1, 1.0, 99, dtype=np.float32).reshape(9, 11)
+    out = oracle.r_l_per_channel(x, oracle.create_blur_kernel(), 3, 0.01)
+    assert np.array_equal(out[0, 0], np.zeros((9, 11), dtype=np.float32))          # all-zero channel stays zero
+    assert np.isfinite(out).all() and (out[0, 1] > 0).all()
+    single = oracle.r_l_per_channel(x[:, 1:2], oracle.create_blur_kernel(), 3, 0.01)
+    assert np.array_equal(single[0, 0], out[0, 1])
+    neg = -x
+    out_neg = oracle.r_l_per_channel(neg, oracle.create_blur_kernel(), 1, 0.01)  # x/blurred > 0 for an all-negative frame
+    assert np.isfinite(out_neg).all()
