@@ -18,10 +18,17 @@
 // epilogue (thread = TMEM lane = pixel: every channel store is a coalesced 128-byte row segment), warp 4
 // issues the MMAs.  Three 16-channel stages, loads prefetched one 32-channel set ahead in registers, two to
 // three CTAs per SM.  Versus the mma.sync version this replaces: 87 / 81 / 101 us -> see DESIGN.md.
+#include <cstdio>
 #include <cstdlib>
 
 #include "spei_common.cuh"
 #include "tc_ptx.cuh"
+
+#ifdef SPEI_FUSE_PROF   // in-kernel clock64 accounting of who waits for whom (experiments only)
+#define FPROF_T(acc_, stmt) { const long long c0_ = clock64(); stmt; acc_ += clock64() - c0_; }
+#else
+#define FPROF_T(acc_, stmt) { stmt; }
+#endif
 
 namespace spei {
 
@@ -288,7 +295,7 @@ fuse_level_tc_kernel(const float* __restrict__ dec, const float* __restrict__ tt
 #endif
 constexpr uint32_t kFRawBytes = kFKC * kFM * 4;           // 8192: one raw activation box
 constexpr int kFOutCh = 16;                               // channels per epilogue staging pass
-constexpr int kFTmaThreads = 320;
+
 
 template <int C>
 struct FuseTmaSmem {
@@ -296,6 +303,11 @@ struct FuseTmaSmem {
   static constexpr int kFRaw = C == 128 ? 5 : 4;                  // raw TMA ring depth (C = 128: one CTA per SM, deeper rings)
   static constexpr int kFU = C == 128 ? 3 : 2;                    // UMMA-layout ring depth
   static constexpr int kCtasPerSm = C == 128 ? 1 : 2;
+  // converter warps per CTA: thread = (pixel, channel part).  C = 128 runs one CTA per SM, so it gets 8 (two threads
+  // per pixel, 8 of the stage's 16 channels each): the converter chain was the longest stage of its pipeline
+  static constexpr int kConvWarps = C == 128 ? 8 : 4;
+  static constexpr int kSplit = kConvWarps / 4;
+  static constexpr int kThreads = (kConvWarps + 6) * 32;
   static constexpr uint32_t kRaw = 0;
   static constexpr uint32_t kWBox = C * kFKC * 4;                 // raw weight box [C rows][16 k] fp32
   static constexpr uint32_t kRawStage = kFRawBytes + kWBox;       // X box + W box per TMA stage
@@ -307,13 +319,15 @@ struct FuseTmaSmem {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kFTmaThreads, FuseTmaSmem<C>::kCtasPerSm)
+__global__ void __launch_bounds__(FuseTmaSmem<C>::kThreads, FuseTmaSmem<C>::kCtasPerSm)
 fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_constant__ CUtensorMap tm_t,
                       const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ dec, const float* __restrict__ S, const float* __restrict__ weight,
                       const float* __restrict__ bias, float* __restrict__ out, int n_items, int h, int w, int scale) {
   using L = FuseTcSmem<C>;
   using SM = FuseTmaSmem<C>;
   constexpr int kFRaw = SM::kFRaw, kFU = SM::kFU;
+  constexpr int CW = SM::kConvWarps, kSplit = SM::kSplit, kConvThreads = CW * 32;
+  constexpr int kChunks = kFKC / 4 / kSplit;      // 4-channel chunks of a stage per converter thread
   int* error_flag = &g_fuse_watchdog;
   constexpr int K = 2 * C, NCH = K / kFKC;
   constexpr uint32_t kCols = 2 * C < 32 ? 32 : 2 * C;   // two accumulators
@@ -331,15 +345,15 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
   const long long tpi = (long long)((plane + kFM - 1) / kFM), total = tpi * n_items;
 
   if (t == 0) {
-    for (int s = 0; s < kFRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, kFM); }
-    for (int s = 0; s < kFU; ++s) { mbar_init(bar_ufull + 8 * s, kFM); mbar_init(bar_uempty + 8 * s, 1); }
+    for (int s = 0; s < kFRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, kConvThreads); }
+    for (int s = 0; s < kFU; ++s) { mbar_init(bar_ufull + 8 * s, kConvThreads); mbar_init(bar_uempty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, kFM); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dec) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_t) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   }
-  if (warp == 4) {
+  if (warp == CW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -348,49 +362,52 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================== convert (thread = pixel; threads < C also convert one weight row) ==================
-    const int px = t;
+  if (warp < CW) {
+    // ====== convert (thread = pixel x channel part; threads with px < C also convert their part of weight row px) ======
+    const int px = t & (kFM - 1), part = t / kFM;   // part < kSplit: chunks [part * kChunks, (part + 1) * kChunks) of the stage
     const bool wrow = px < C;
     long long tile = blockIdx.x;
     int g = 0;
+    [[maybe_unused]] long long pf_t0 = clock64(), pf_rfull = 0, pf_uempty = 0;
 #pragma unroll 1
     for (; tile < total; tile += gridDim.x) {
 #pragma unroll 1
       for (int kc = 0; kc < NCH; ++kc, ++g) {
         const int r = g % kFRaw, s = g % kFU;
-        FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kFRaw) & 1), error_flag);
+        FPROF_T(pf_rfull, FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kFRaw) & 1), error_flag));
         const float* rbox = raw + (size_t)r * (SM::kRawStage / 4);
-        float x[kFKC];
+        float x[4 * kChunks];
 #pragma unroll
-        for (int c = 0; c < kFKC; ++c) x[c] = rbox[c * kFM + px];
-        // weight row px of this stage: 4 x 16 B at a 64-byte thread stride.  Read in the fixed order j the 8 threads
-        // of a 128-bit shared-memory phase hit only two 4-bank groups (4-way conflict; ncu: 45 % of the kernel's LSU
-        // wavefronts were conflicts), so thread px starts at chunk (px >> 1) & 3 and wraps: all 8 groups distinct.
-        // The chunk index only enters address arithmetic (load here, store below), never a register index.
-        const int jrot = (px >> 1) & 3;
-        float4 wv[kFKC / 4];
+        for (int c = 0; c < 4 * kChunks; ++c) x[c] = rbox[(part * 4 * kChunks + c) * kFM + px];
+        // weight row px of this stage: 16-byte chunks at a 64-byte thread stride.  Read in a fixed chunk order the 8
+        // threads of a 128-bit shared-memory phase hit only two 4-bank groups (4-way conflict; ncu: 45 % of the kernel's
+        // LSU wavefronts were conflicts), so thread px starts at chunk (px >> 1) % kChunks of its part and wraps.  The
+        // chunk index only enters address arithmetic (load here, store below), never a register index.
+        const int jrot = (px >> 1) & (kChunks - 1);
+        float4 wv[kChunks];
 #pragma unroll
-        for (int j = 0; j < kFKC / 4; ++j)
-          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[(j + jrot) & 3] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kChunks; ++j)
+          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[part * kChunks + ((j + jrot) & (kChunks - 1))]
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
         // generic-proxy reads must be ordered before the async-proxy (TMA) refill of this box: without this
         // fence the refill raced with the reads (measured: sporadic wrong tiles at C = 128, where the ring wraps)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(bar_rempty + 8 * r);
-        if (g >= kFU) FUSE_WAIT(bar_uempty + 8 * s, (uint32_t)((g / kFU - 1) & 1), error_flag);
+        if (g >= kFU) FPROF_T(pf_uempty, FUSE_WAIT(bar_uempty + 8 * s, (uint32_t)((g / kFU - 1) & 1), error_flag));
         const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
 #ifndef SPEI_FUSE_NO_CONV
 #pragma unroll
-        for (int j = 0; j < kFKC / 4; ++j) {
+        for (int j = 0; j < kChunks; ++j) {
           const float x4[4] = {x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]};
           uint4 hi, lo;
           ft_split4(x4, hi, lo);
-          st_shared_v4(a_hi + j * L::kALBO + px * 16, hi);
-          st_shared_v4(a_lo + j * L::kALBO + px * 16, lo);
+          const uint32_t ja = (uint32_t)(part * kChunks + j);
+          st_shared_v4(a_hi + ja * L::kALBO + px * 16, hi);
+          st_shared_v4(a_lo + ja * L::kALBO + px * 16, lo);
           if (wrow) {
             const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
             ft_split4(w4, hi, lo);
-            const uint32_t jj = (uint32_t)((j + jrot) & 3);
+            const uint32_t jj = (uint32_t)(part * kChunks + ((j + jrot) & (kChunks - 1)));
             st_shared_v4(b_hi + jj * L::kBLBO + px * 16, hi);
             st_shared_v4(b_lo + jj * L::kBLBO + px * 16, lo);
           }
@@ -404,19 +421,23 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
         mbar_arrive(bar_ufull + 8 * s);
       }
     }
-  } else if (warp == 4) {
+#ifdef SPEI_FUSE_PROF
+    if (blockIdx.x == 3 && (t == 0 || t == 100)) printf("C=%d conv t%d: total %lld wait_rfull %lld wait_uempty %lld stages %d\n", C, t, clock64() - pf_t0, pf_rfull, pf_uempty, g);
+#endif
+  } else if (warp == CW) {
     // ======================================== MMA issuer ========================================
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
       int g = 0, it = 0;
+      [[maybe_unused]] long long pf_t0 = clock64(), pf_aempty = 0, pf_ufull = 0;
       for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
         const uint32_t ab = it & 1;
-        if (it >= 2) FUSE_WAIT(bar_aempty + 8 * ab, (uint32_t)((it / 2 - 1) & 1), error_flag);
+        if (it >= 2) FPROF_T(pf_aempty, FUSE_WAIT(bar_aempty + 8 * ab, (uint32_t)((it / 2 - 1) & 1), error_flag));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * C;
         for (int kc = 0; kc < NCH; ++kc, ++g) {
           const int s = g % kFU;
-          FUSE_WAIT(bar_ufull + 8 * s, (uint32_t)((g / kFU) & 1), error_flag);
+          FPROF_T(pf_ufull, FUSE_WAIT(bar_ufull + 8 * s, (uint32_t)((g / kFU) & 1), error_flag));
           tc_fence_after();
           const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
 #pragma unroll
@@ -435,29 +456,36 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
         }
         tc_commit(bar_afull + 8 * ab);
       }
+#ifdef SPEI_FUSE_PROF
+      if (blockIdx.x == 3) printf("C=%d mma: total %lld wait_aempty %lld wait_ufull %lld tiles %d\n", C, clock64() - pf_t0, pf_aempty, pf_ufull, it);
+#endif
     }
-  } else if (warp == 5) {
+  } else if (warp == CW + 1) {
     // ======================================== TMA producer ========================================
     if (lane == 0) {
       int g = 0;
+      [[maybe_unused]] long long pf_t0 = clock64(), pf_rempty = 0;
       for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int n = (int)(tile / tpi);
         const int p0 = (int)((tile - (long long)n * tpi) * kFM);
         for (int kc = 0; kc < NCH; ++kc, ++g) {
           const int r = g % kFRaw;
-          if (g >= kFRaw) FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kFRaw - 1) & 1), error_flag);
+          if (g >= kFRaw) FPROF_T(pf_rempty, FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kFRaw - 1) & 1), error_flag));
           mbar_arrive_expect_tx(bar_rfull + 8 * r, SM::kRawStage);
           const int ch0 = kc * kFKC;
           tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage, ch0 < C ? &tm_dec : &tm_t, bar_rfull + 8 * r, p0, n * C + (ch0 < C ? ch0 : ch0 - C));
           tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage + kFRawBytes, &tm_w, bar_rfull + 8 * r, ch0, 0);  // weight columns ch0..ch0+15
         }
       }
+#ifdef SPEI_FUSE_PROF
+      if (blockIdx.x == 3) printf("C=%d tma: total %lld wait_rempty %lld\n", C, clock64() - pf_t0, pf_rempty);
+#endif
     }
   } else {
     // ================================ epilogue (thread = TMEM lane = pixel) ================================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int px = q * 32 + lane;
-    const int te = (warp - 6) * 32 + lane;  // 0..127: cooperative row mapping of the store phase
+    const int te = (warp - (CW + 2)) * 32 + lane;  // 0..127: cooperative row mapping of the store phase
     auto soft_weight = [&](long long tile) {  // bicubic upsampled S at this thread's pixel of `tile`
       const int n = (int)(tile / tpi);
       const size_t p = (size_t)(tile - (long long)n * tpi) * kFM + px;
@@ -484,6 +512,7 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
     float4 dnext[kFOutCh / 4];
     load_residual(tile, 0, dnext);
     int it = 0, pass = 0;
+    [[maybe_unused]] long long pf_t0 = clock64(), pf_afull = 0;
 #pragma unroll 1
     for (; tile < total; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1;
@@ -491,7 +520,7 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
       const int n = (int)(tile / tpi);
       const size_t p0 = (size_t)(tile - (long long)n * tpi) * kFM;
       const bool rin = p0 + px4 < plane;
-      FUSE_WAIT(bar_afull + 8 * ab, (uint32_t)((it / 2) & 1), error_flag);
+      FPROF_T(pf_afull, FUSE_WAIT(bar_afull + 8 * ab, (uint32_t)((it / 2) & 1), error_flag));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ab * C + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -526,12 +555,342 @@ fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_c
       mbar_arrive(bar_aempty + 8 * ab);   // this accumulator may be overwritten by the tile after next
       sw = sw_next;
     }
+#ifdef SPEI_FUSE_PROF
+    if (blockIdx.x == 3 && te == 0) printf("C=%d epi: total %lld wait_afull %lld tiles %d\n", C, clock64() - pf_t0, pf_afull, it);
+#endif
   }
 
   __syncthreads();
-  if (warp == 4) {
+  if (warp == CW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// v3 ("TS"): the activations are the A operand FROM TENSOR MEMORY.
+//
+// clock64 accounting of the kernel above (SPEI_FUSE_PROF, round 1): the converter threads are busy 87 % of the time, the
+// MMA issuer waits for operands 60 %, the TMA producer waits for a free slot 86 %; every activation float crosses
+// shared memory as 4 B TMA write + 4 B LDS + 8 B hi/lo STS + 12 B UMMA operand reads (28 B per 4 B of HBM traffic), and
+// the weights again per 128-pixel tile: the shared-memory pipe, not HBM, bounds that design.  Here
+//   * the converter thread (= pixel = TMEM lane) reads its 16 channels of the raw TMA box, splits them and writes hi / lo
+//     straight into a ring of A tiles in tensor memory (tcgen05.st, 32 columns per stage); the MMA reads A from there
+//     (tcgen05.mma [d], [a], b-desc): per activation float shared memory now carries 4 B TMA write + 4 B LDS;
+//   * for C <= 64 the hi / lo weight tiles of ALL stages are converted once per CTA and stay resident in shared memory
+//     (64 KB / 16 KB); C = 128 (256 KB of hi + lo) keeps the per-stage conversion of the 16 weight columns, with two
+//     converter threads per pixel.
+// TMEM columns: [accumulator 0 | accumulator 1 | A ring: kU x (16 hi + 16 lo)].
+// ---------------------------------------------------------------------------------------------------------
+template <int C>
+struct FuseTsCfg {
+  static constexpr bool kResidentW = C <= 64;
+  static constexpr int kConvWarps = C == 128 ? 8 : 4;
+  static constexpr int kSplit = kConvWarps / 4;
+  static constexpr int kThreads = (kConvWarps + 6) * 32;
+  static constexpr int kCtasPerSm = C == 128 ? 1 : 2;
+  static constexpr int kRaw = C == 128 ? 5 : (C == 64 ? 3 : 4);   // raw TMA ring depth
+  static constexpr int kE = C == 64 ? 3 : 4;                       // residual / output box ring depth (epilogue)
+  static constexpr int kU = 4;                                     // A ring depth in TMEM (= B ring depth for C = 128)
+  static constexpr int NCH = 2 * C / kFKC;
+  static constexpr uint32_t kBLBO = C * 16;                        // stride between 4-channel core-matrix columns of W
+  static constexpr uint32_t kBBytes = (kFKC / 4) * kBLBO;          // one hi (or lo) weight tile of a stage
+  static constexpr uint32_t kWBox = kResidentW ? 0u : (uint32_t)(C * kFKC * 4);
+  static constexpr uint32_t kRawStage = kFRawBytes + kWBox;
+  static constexpr uint32_t kOffB = kRaw * kRawStage;
+  static constexpr uint32_t kOffOut = kOffB + (uint32_t)(kResidentW ? NCH : kU) * 2 * kBBytes;
+  static constexpr uint32_t kOutBox = kFOutCh * kFM * 4;           // [16 channel][128 pixel] fp32, the TMA box of dec / out
+  static constexpr uint32_t kOffBars = kOffOut + kE * kOutBox;
+  static constexpr uint32_t kNumBars = 2 * kRaw + 2 * kU + 4 + kE;
+  static constexpr uint32_t kTotal = kOffBars + 8 * kNumBars + 16;
+  static constexpr uint32_t kACol0 = 2 * C;
+  static constexpr uint32_t kColsNeeded = 2 * C + kU * 32;
+  static constexpr uint32_t kCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
+};
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int C>
+__global__ void __launch_bounds__(FuseTsCfg<C>::kThreads, FuseTsCfg<C>::kCtasPerSm)
+fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_constant__ CUtensorMap tm_t,
+                     const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ S,
+                     const float* __restrict__ weight, const float* __restrict__ bias, int n_items, int h, int w, int scale) {
+  using F = FuseTsCfg<C>;
+  constexpr int kRaw = F::kRaw, kU = F::kU, kE = F::kE, CW = F::kConvWarps, kConvThreads = CW * 32, NCH = F::NCH;
+  constexpr int kCh = kFKC / F::kSplit;          // channels of a stage per converter thread (16 or 8)
+  constexpr int K = 2 * C;
+  int* error_flag = &g_fuse_watchdog;
+  extern __shared__ __align__(1024) uint8_t fsmem[];
+  const uint32_t s0 = smem_u32(fsmem);
+  const uint32_t bar_rfull = s0 + F::kOffBars, bar_rempty = bar_rfull + 8 * kRaw, bar_afull = bar_rempty + 8 * kRaw,
+                 bar_aempty = bar_afull + 8 * kU, bar_dfull = bar_aempty + 8 * kU, bar_dempty = bar_dfull + 16,
+                 bar_efull = bar_dempty + 16;   // residual box of an epilogue pass has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fsmem + F::kOffBars + 8 * F::kNumBars);
+  float* ostage = reinterpret_cast<float*>(fsmem + F::kOffOut);   // [kE][16 ch][128 px]
+  const float* raw = reinterpret_cast<const float*>(fsmem);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int hs = h * scale, wsz = w * scale;
+  const size_t plane = (size_t)hs * wsz;
+  const long long tpi = (long long)((plane + kFM - 1) / kFM), total = tpi * n_items;
+
+  if (t == 0) {
+    for (int s = 0; s < kRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, kConvThreads); }
+    for (int s = 0; s < kU; ++s) { mbar_init(bar_afull + 8 * s, kConvThreads); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_dempty + 8 * s, kFM); }
+    for (int s = 0; s < kE; ++s) mbar_init(bar_efull + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dec) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_t) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_out) : "memory");
+    if (!F::kResidentW) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+  }
+  if (warp == CW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(F::kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (F::kResidentW) {
+    // hi / lo weight tiles of every stage, once per CTA: element (o, k) -> stage k/16, chunk (k%16)/4, row o.
+    // Consecutive threads take consecutive rows o (conflict-free 16-byte stores; the strided reads are L2 hits).
+    for (int idx = t; idx < C * (K / 4); idx += F::kThreads) {
+      const int o = idx % C, k4 = idx / C;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(weight + (size_t)o * K) + k4);
+      const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint4 hi, lo;
+      ft_split4(w4, hi, lo);
+      const uint32_t b_hi = s0 + F::kOffB + (uint32_t)(k4 >> 2) * 2 * F::kBBytes + (uint32_t)(k4 & 3) * F::kBLBO + (uint32_t)o * 16;
+      st_shared_v4(b_hi, hi);
+      st_shared_v4(b_hi + F::kBBytes, lo);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < CW) {
+    // ====== convert: thread = (pixel = TMEM lane, channel part) ======
+    const int px = t & (kFM - 1), part = t / kFM;
+    const bool wrow = !F::kResidentW && px < C;
+    const uint32_t a_lane = tmem_base + F::kACol0 + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * kCh);
+    long long tile = blockIdx.x;
+    int g = 0;
+    [[maybe_unused]] long long pf_t0 = clock64(), pf_rfull = 0, pf_aempty = 0;
+#pragma unroll 1
+    for (; tile < total; tile += gridDim.x) {
+#pragma unroll 1
+      for (int kc = 0; kc < NCH; ++kc, ++g) {
+        const int r = g % kRaw, u = g % kU;
+        FPROF_T(pf_rfull, FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kRaw) & 1), error_flag));
+        const float* rbox = raw + (size_t)r * (F::kRawStage / 4);
+        float x[kCh];
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) x[c] = rbox[(part * kCh + c) * kFM + px];
+        constexpr int kWChunks = kCh / 4;          // 16-byte chunks of weight row px this thread converts (C = 128 only)
+        const int jrot = (px >> 1) & (kWChunks - 1);
+        float4 wv[kWChunks];
+        if (!F::kResidentW) {
+#pragma unroll
+          for (int j = 0; j < kWChunks; ++j)
+            wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[part * kWChunks + ((j + jrot) & (kWChunks - 1))]
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // hi = x truncated to TF32, lo = x - hi (exact).  Computing them here consumes every value read from the box, so
+        // the loads have completed before the slot is handed back to the TMA producer (no proxy fence needed for that
+        // write-after-read; the fence cost ~1/4 of the converter's stage time in the shared-memory-operand kernel).
+        uint32_t xhi[kCh], xlo[kCh];
+#pragma unroll
+        for (int i = 0; i < kCh; ++i) {
+          xhi[i] = __float_as_uint(x[i]) & 0xffffe000u;
+          xlo[i] = __float_as_uint(x[i] - __uint_as_float(xhi[i]));
+        }
+        uint4 whi[kWChunks], wlo[kWChunks];
+        if (!F::kResidentW) {
+#pragma unroll
+          for (int j = 0; j < kWChunks; ++j) {
+            const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+            ft_split4(w4, whi[j], wlo[j]);
+          }
+        }
+        mbar_arrive(bar_rempty + 8 * r);
+        if (g >= kU) FPROF_T(pf_aempty, FUSE_WAIT(bar_aempty + 8 * u, (uint32_t)((g / kU - 1) & 1), error_flag));
+        tc_fence_after();
+        // columns [u*32 + c] (hi) and [u*32 + 16 + c] (lo) of this thread's TMEM lane
+#pragma unroll
+        for (int c8 = 0; c8 < kCh / 8; ++c8) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { hi[i] = xhi[8 * c8 + i]; lo[i] = xlo[8 * c8 + i]; }
+          tc_st8(a_lane + (uint32_t)(u * 32 + 8 * c8), hi);
+          tc_st8(a_lane + (uint32_t)(u * 32 + 16 + 8 * c8), lo);
+        }
+        if (!F::kResidentW && wrow) {
+          const uint32_t b_hi = s0 + F::kOffB + (uint32_t)u * 2 * F::kBBytes, b_lo = b_hi + F::kBBytes;
+#pragma unroll
+          for (int j = 0; j < kWChunks; ++j) {
+            const uint32_t jj = (uint32_t)(part * kWChunks + ((j + jrot) & (kWChunks - 1)));
+            st_shared_v4(b_hi + jj * F::kBLBO + px * 16, whi[j]);
+            st_shared_v4(b_lo + jj * F::kBLBO + px * 16, wlo[j]);
+          }
+        }
+        tc_wait_st();
+        if (!F::kResidentW) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight tile stores -> MMA (async proxy)
+        tc_fence_before();
+        mbar_arrive(bar_afull + 8 * u);
+      }
+    }
+#ifdef SPEI_FUSE_PROF
+    if (blockIdx.x == 3 && (t == 0 || t == 100)) printf("TS C=%d conv t%d: total %lld wait_rfull %lld wait_aempty %lld stages %d\n", C, t, clock64() - pf_t0, pf_rfull, pf_aempty, g);
+#endif
+  } else if (warp == CW) {
+    // ======================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
+      int g = 0, it = 0;
+      [[maybe_unused]] long long pf_t0 = clock64(), pf_dempty = 0, pf_afull = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1;
+        if (it >= 2) FPROF_T(pf_dempty, FUSE_WAIT(bar_dempty + 8 * ab, (uint32_t)((it / 2 - 1) & 1), error_flag));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * C;
+        for (int kc = 0; kc < NCH; ++kc, ++g) {
+          const int u = g % kU;
+          FPROF_T(pf_afull, FUSE_WAIT(bar_afull + 8 * u, (uint32_t)((g / kU) & 1), error_flag));
+          tc_fence_after();
+          const uint32_t b_hi = s0 + F::kOffB + (uint32_t)(F::kResidentW ? kc : u) * 2 * F::kBBytes, b_lo = b_hi + F::kBBytes;
+          const uint32_t a_hi = tmem_base + F::kACol0 + (uint32_t)(u * 32), a_lo = a_hi + 16;
+#pragma unroll
+          for (uint32_t kk = 0; kk < kFKC / 8; ++kk) {
+            const uint64_t dbh = umma_desc_kmajor(b_hi + kk * 2 * F::kBLBO, F::kBLBO, 128);
+            const uint64_t dbl = umma_desc_kmajor(b_lo + kk * 2 * F::kBLBO, F::kBLBO, 128);
+            tc_mma_tf32_ts(d_tmem, a_lo + kk * 8, dbh, idesc, (kc | kk) != 0);  // small terms first
+            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, dbl, idesc, 1u);
+            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, dbh, idesc, 1u);
+          }
+          tc_commit(bar_aempty + 8 * u);
+        }
+        tc_commit(bar_dfull + 8 * ab);
+      }
+#ifdef SPEI_FUSE_PROF
+      if (blockIdx.x == 3) printf("TS C=%d mma: total %lld wait_dempty %lld wait_afull %lld tiles %d\n", C, clock64() - pf_t0, pf_dempty, pf_afull, it);
+#endif
+    }
+  } else if (warp == CW + 1) {
+    // ======================================== TMA producer ========================================
+    if (lane == 0) {
+      int g = 0;
+      [[maybe_unused]] long long pf_t0 = clock64(), pf_rempty = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n = (int)(tile / tpi);
+        const int p0 = (int)((tile - (long long)n * tpi) * kFM);
+        for (int kc = 0; kc < NCH; ++kc, ++g) {
+          const int r = g % kRaw;
+          if (g >= kRaw) FPROF_T(pf_rempty, FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kRaw - 1) & 1), error_flag));
+          mbar_arrive_expect_tx(bar_rfull + 8 * r, F::kRawStage);
+          const int ch0 = kc * kFKC;
+          tma_load_2d(s0 + r * F::kRawStage, ch0 < C ? &tm_dec : &tm_t, bar_rfull + 8 * r, p0, n * C + (ch0 < C ? ch0 : ch0 - C));
+          if (!F::kResidentW) tma_load_2d(s0 + r * F::kRawStage + kFRawBytes, &tm_w, bar_rfull + 8 * r, ch0, 0);  // weight columns ch0..ch0+15
+        }
+      }
+#ifdef SPEI_FUSE_PROF
+      if (blockIdx.x == 3) printf("TS C=%d tma: total %lld wait_rempty %lld\n", C, clock64() - pf_t0, pf_rempty);
+#endif
+    }
+  } else {
+    // ================================ epilogue (thread = TMEM lane = pixel) ================================
+    // One pass = 16 output channels of a tile = one [16 channel][128 pixel] box.  The residual box of `dec` arrives by
+    // TMA into a ring slot (prefetched kE - 1 passes ahead: the shared-memory-operand kernel read it with LDGs one
+    // pass ahead and was bound by that latency), every thread adds (acc + bias) * soft weight to its pixel in place,
+    // and one thread stores the box with a TMA store.  Partial last tiles are clipped by the tensor maps.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int px = q * 32 + lane;
+    const bool elected = warp == CW + 2 && lane == 0;
+    auto soft_weight = [&](long long tile) {  // bicubic upsampled S at this thread's pixel of `tile`
+      const int n = (int)(tile / tpi);
+      const size_t p = (size_t)(tile - (long long)n * tpi) * kFM + px;
+      if (p >= plane) return 0.f;
+      const int oy = (int)(p / wsz), ox = (int)(p % wsz);
+      const float* S_n = S + (size_t)n * h * w;
+      return scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : ft_bicubic(S_n, h, w, oy, ox, 1.0f / (float)scale);
+    };
+    constexpr int kPasses = C / kFOutCh;
+    // residual box of global pass number `pn` (tile = blockIdx.x + (pn / kPasses) * gridDim.x, channels (pn % kPasses) * 16)
+    auto issue_residual = [&](long long pn) {
+      const long long tl = (long long)blockIdx.x + (pn / kPasses) * (long long)gridDim.x;
+      if (tl >= total) return;
+      const int n = (int)(tl / tpi);
+      const int p0 = (int)((tl - (long long)n * tpi) * kFM);
+      const int e = (int)(pn % kE);
+      mbar_arrive_expect_tx(bar_efull + 8 * e, F::kOutBox);
+      tma_load_2d(s0 + F::kOffOut + e * F::kOutBox, &tm_dec, bar_efull + 8 * e, p0, n * C + (int)(pn % kPasses) * kFOutCh);
+    };
+    if (elected) {
+      for (int i = 0; i < kE - 1; ++i) issue_residual(i);
+    }
+    long long tile = blockIdx.x;
+    float sw = tile < total ? soft_weight(tile) : 0.f;
+    int it = 0;
+    long long pass = 0;
+    [[maybe_unused]] long long pf_t0 = clock64(), pf_dfull = 0, pf_efull = 0;
+#pragma unroll 1
+    for (; tile < total; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1;
+      const float sw_next = tile + gridDim.x < total ? soft_weight(tile + gridDim.x) : 0.f;  // taps in flight during this tile
+      const int n = (int)(tile / tpi);
+      const int p0 = (int)((tile - (long long)n * tpi) * kFM);
+      FPROF_T(pf_dfull, FUSE_WAIT(bar_dfull + 8 * ab, (uint32_t)((it / 2) & 1), error_flag));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * C + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += kFOutCh, ++pass) {
+        const int e = (int)(pass % kE);
+        float* ost = ostage + e * (kFOutCh * kFM);
+        uint32_t a[16];
+        tc_ld16(taddr + c0, a);
+        FPROF_T(pf_efull, FUSE_WAIT(bar_efull + 8 * e, (uint32_t)((pass / kE) & 1), error_flag));
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ost[i * kFM + px] = ost[i * kFM + px] + (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the TMA store (async proxy)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (elected) {
+          tma_store_2d(&tm_out, s0 + F::kOffOut + e * F::kOutBox, p0, n * C + c0);
+          bulk_commit_group();
+          // the slot of the PREVIOUS pass is free once its store has read shared memory: refill it kE - 1 passes ahead
+          bulk_wait_group_read<1>();
+          issue_residual(pass >= 1 ? pass - 1 + kE : kE - 1);   // (pass 0: the one slot the prologue left empty)
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_dempty + 8 * ab);   // this accumulator may be overwritten by the tile after next
+      sw = sw_next;
+    }
+    if (elected) bulk_wait_group<0>();     // all output boxes are in global memory before the CTA exits
+#ifdef SPEI_FUSE_PROF
+    if (blockIdx.x == 3 && px == 0) printf("TS C=%d epi: total %lld wait_dfull %lld wait_efull %lld tiles %d\n", C, clock64() - pf_t0, pf_dfull, pf_efull, it);
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == CW) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(F::kCols) : "memory");
   }
 }
 
@@ -568,6 +927,21 @@ static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, c
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level weight) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
   }
+  static const bool ss = getenv("SPEI_FUSE_SS") != nullptr;   // A/B switch: the shared-memory-operand kernel (v2)
+  if (!ss) {
+    const int smem = (int)FuseTsCfg<C>::kTotal;
+    SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    int dev = 0, sms = 0;
+    SPEI_CUDA(cudaGetDevice(&dev));
+    SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTsCfg<C>::kCtasPerSm;
+    CUtensorMap tmo;
+    if ((rc = make_plane_map(enc, &tmo, out, (size_t)n * C, plane))) return rc;
+    fuse_level_ts_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTsCfg<C>::kThreads, smem, st>>>(tmd, tmt, tmw, tmo, S, weight, bias, n, h, w, scale);
+    SPEI_CUDA(cudaGetLastError());
+    return SPEI_OK;
+  }
   const int smem = (int)FuseTmaSmem<C>::kTotal;
   SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -575,7 +949,7 @@ static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, c
   SPEI_CUDA(cudaGetDevice(&dev));
   SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTmaSmem<C>::kCtasPerSm;
-  fuse_level_tma_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), kFTmaThreads, smem, st>>>(tmd, tmt, tmw, dec, S, weight, bias, out, n, h, w, scale);
+  fuse_level_tma_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTmaSmem<C>::kThreads, smem, st>>>(tmd, tmt, tmw, dec, S, weight, bias, out, n, h, w, scale);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }
