@@ -35,7 +35,7 @@ import torch  # noqa: E402
 H, W, C3 = 180, 320, 128                      # lv3 grid of a 1280x720 frame (speinet.py:124-127)
 L = H * W
 FLOPS_RELEVANCE = 2.0 * L * L * 9 * C3        # 7.644 TFLOP
-KERNELS_PER_STEP = 3 + 4 + 1 + 5 + 4 + 3      # stage q, stage k (incl. padding zero-fill), tcgen05, rescore group, gather/fold x3 (+ lv2 staging), fuse x3
+KERNELS_PER_STEP = 3 + 1 + 5 + 4 + 3          # staging (zero padding, transpose, norms: both operands per launch), tcgen05, rescore group, gather/fold x3 (+ lv2 staging), fuse x3
 WORKLOAD = "searchtransfer_fusion_1280x720_1ref"
 
 

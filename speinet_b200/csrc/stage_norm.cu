@@ -17,12 +17,34 @@ namespace spei {
 
 constexpr int kPx = 32;  // pixels (consecutive x) per block
 
+// One operand (query set or key set) of the staging pass
+struct StageOp {
+  const float* x;          // [nimg][128][H][W] fp32
+  __nv_bfloat16* bf;       // [nimg][16][Vpad][Upad][8]
+  float* x32;              // [nimg][H][W][128]
+  float* ss;               // [nimg][H][W] per-pixel sum of squares
+  float* r;                // [nimg][H*W] reciprocal patch norms
+  float* rkpad;            // keys only (else nullptr): tile-padded reciprocal norms, NaN outside the image
+  int nimg, H, W, orient, U, V, Upad, Vpad;
+  int UT, VT, border;      // rkpad geometry
+};
+
+// grid: (ceil(maxW/32), maxH, nimg_q + nimg_k): both operands in ONE launch (the staging pass was 7 launches of
+// 2-17 us each; the gaps between them were a quarter of its time)
 __global__ void __launch_bounds__(256)
-stage_transpose_kernel(const float* __restrict__ x, int H, int W, int orient, int Upad, int Vpad,
-                       __nv_bfloat16* __restrict__ bf, float* __restrict__ x32, float* __restrict__ ss) {
+stage_transpose_kernel(const StageOp oq, const StageOp ok) {
   __shared__ float tile[kC3][kPx + 1];
   __shared__ float part[8][kPx];
-  const int img = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kPx;
+  const bool is_k = (int)blockIdx.z >= oq.nimg;
+  const StageOp& o = is_k ? ok : oq;
+  const int img = is_k ? blockIdx.z - oq.nimg : blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kPx;
+  const int H = o.H, W = o.W;
+  if (y >= H || x0 >= W) return;
+  const float* __restrict__ x = o.x;
+  __nv_bfloat16* __restrict__ bf = o.bf;
+  float* __restrict__ x32 = o.x32;
+  float* __restrict__ ss = o.ss;
+  const int orient = o.orient, Upad = o.Upad, Vpad = o.Vpad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t plane = (size_t)H * W;
   const float* src = x + (size_t)img * kC3 * plane + (size_t)y * W + x0;
@@ -49,8 +71,8 @@ stage_transpose_kernel(const float* __restrict__ x, int H, int W, int orient, in
       for (int i = 0; i < 8; ++i) v[i] = __float2bfloat16_rn(tile[cg * 8 + i][px]);
       const int xx = x0 + px;
       const int u = orient == 0 ? xx : y, vv = orient == 0 ? y : xx;
-      const size_t o = ((((size_t)img * kCG + cg) * Vpad + (vv + 1)) * Upad + (u + 1)) * 8;
-      *reinterpret_cast<uint4*>(bf + o) = *reinterpret_cast<const uint4*>(v);
+      const size_t off = ((((size_t)img * kCG + cg) * Vpad + (vv + 1)) * Upad + (u + 1)) * 8;
+      *reinterpret_cast<uint4*>(bf + off) = *reinterpret_cast<const uint4*>(v);
     }
   }
   // per-pixel sum of squares over the 128 channels (fixed order: 8 partials of 16 channels)
@@ -82,74 +104,73 @@ __device__ __forceinline__ float patch_rnorm(const float* __restrict__ ss, int H
   return 1.0f / fmaxf(sqrtf(s), 1e-12f);  // F.normalize: v / max(||v||, eps)
 }
 
+// rq, rk and the tile-padded key norms in ONE launch: thread i covers [q positions | k positions | padded k positions]
 __global__ void __launch_bounds__(256)
-patch_norm_kernel(const float* __restrict__ ss, int nimg, int H, int W, float* __restrict__ r) {
-  const size_t plane = (size_t)H * W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= plane * nimg) return;
-  const int img = (int)(i / plane), rem = (int)(i % plane);
-  r[i] = patch_rnorm(ss + (size_t)img * plane, H, W, rem / W, rem % W);
-}
-
-__global__ void __launch_bounds__(256)
-key_norm_padded_kernel(const float* __restrict__ ss, int nimg, int H, int W, int orient, int UT, int VT, int border,
-                       float* __restrict__ rkpad) {
-  const size_t per = (size_t)UT * VT;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per * nimg) return;
+patch_norms_kernel(const StageOp oq, const StageOp ok) {
+  const size_t nq = (size_t)oq.nimg * oq.H * oq.W, nk = (size_t)ok.nimg * ok.H * ok.W;
+  const size_t per = (size_t)ok.UT * ok.VT, np = ok.rkpad ? per * ok.nimg : 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq + nk) {
+    const StageOp& o = i < nq ? oq : ok;
+    if (i >= nq) i -= nq;
+    const size_t plane = (size_t)o.H * o.W;
+    const int img = (int)(i / plane), rem = (int)(i % plane);
+    o.r[i] = patch_rnorm(o.ss + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
+    return;
+  }
+  i -= nq + nk;
+  if (i >= np) return;
   const int img = (int)(i / per), rem = (int)(i % per);
-  const int v = rem / UT, u = rem % UT - border;
-  const int x = orient == 0 ? u : v, y = orient == 0 ? v : u;
+  const int v = rem / ok.UT, u = rem % ok.UT - ok.border;
+  const int x = ok.orient == 0 ? u : v, y = ok.orient == 0 ? v : u;
   float out = __int_as_float(0x7fc00000);  // NaN: padded keys never compare greater
-  if (u >= 0 && x < W && y < H) out = patch_rnorm(ss + (size_t)img * H * W, H, W, y, x);
-  rkpad[i] = out;
+  if (u >= 0 && x < ok.W && y < ok.H) out = patch_rnorm(ok.ss + (size_t)img * ok.H * ok.W, ok.H, ok.W, y, x);
+  ok.rkpad[i] = out;
 }
 
 // Zeroes only what stage_transpose_kernel does not write: the 1-position border and the tile padding of the
-// [Vpad][Upad] planes (3-5 % of the buffer; a full cudaMemset of both operands cost ~10 us per call at 720p).
+// [Vpad][Upad] planes of both operands (3-5 % of the buffers; a full cudaMemset cost ~10 us per call at 720p).
+// grid: (ceil(max plane / 256), 64 plane slices, 2 operands)
 __global__ void __launch_bounds__(256)
-zero_padding_kernel(__nv_bfloat16* __restrict__ bf, int nimg, int U, int V, int Upad, int Vpad) {
-  const int per = Upad * Vpad;
+zero_padding_kernel(const StageOp oq, const StageOp ok) {
+  const StageOp& o = blockIdx.z ? ok : oq;
+  const int per = o.Upad * o.Vpad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per) return;
-  const int v = i / Upad, u = i - v * Upad;
-  if (u >= 1 && u <= U && v >= 1 && v <= V) return;   // interior: written by the transpose kernel
+  const int v = i / o.Upad, u = i - v * o.Upad;
+  if (u >= 1 && u <= o.U && v >= 1 && v <= o.V) return;   // interior: written by the transpose kernel
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (int pl = blockIdx.y; pl < nimg * kCG; pl += gridDim.y)
-    *reinterpret_cast<uint4*>(bf + ((size_t)pl * per + i) * 8) = z;
+  for (int pl = blockIdx.y; pl < o.nimg * kCG; pl += gridDim.y)
+    *reinterpret_cast<uint4*>(o.bf + ((size_t)pl * per + i) * 8) = z;
 }
 
-static int stage_operand(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32,
-                         float* ss, float* r, float* rkpad, cudaStream_t st) {
-  {
-    const int per = o.Upad * o.Vpad;
-    const int planes = nimg * kCG;
-    zero_padding_kernel<<<dim3((per + 255) / 256, planes < 64 ? planes : 64), 256, 0, st>>>(bf, nimg, o.U, o.V, o.Upad, o.Vpad);
-    SPEI_CUDA(cudaGetLastError());
-  }
-  dim3 grid((W + kPx - 1) / kPx, H, nimg);
-  stage_transpose_kernel<<<grid, 256, 0, st>>>(x, H, W, o.orient, o.Upad, o.Vpad, bf, x32, ss);
-  SPEI_CUDA(cudaGetLastError());
-  const size_t tot = (size_t)nimg * H * W;
-  patch_norm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ss, nimg, H, W, r);
-  SPEI_CUDA(cudaGetLastError());
-  if (rkpad) {
-    // dense tiling: [tv*Ny][tu*8]; tap-sharing tiling: [tv*Ny][Upad] with the staged image's 1-position u border
-    const bool shared = o.tile_u == kSTileU;
-    const int UT = shared ? o.Upad : o.tu * kTileU, VT = o.tv * o.tile_v;
-    const size_t totp = (size_t)nimg * UT * VT;
-    key_norm_padded_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(ss, nimg, H, W, o.orient, UT, VT, shared ? 1 : 0, rkpad);
-    SPEI_CUDA(cudaGetLastError());
-  }
-  return SPEI_OK;
+static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* r,
+                       float* rkpad) {
+  StageOp s{};
+  s.x = x; s.bf = bf; s.x32 = x32; s.ss = ss; s.r = r; s.rkpad = rkpad;
+  s.nimg = nimg; s.H = H; s.W = W; s.orient = o.orient; s.U = o.U; s.V = o.V; s.Upad = o.Upad; s.Vpad = o.Vpad;
+  // dense tiling: [tv*Ny][tu*8]; tap-sharing tiling: [tv*Ny][Upad] with the staged image's 1-position u border
+  const bool shared = o.tile_u == kSTileU;
+  s.UT = shared ? o.Upad : o.tu * kTileU; s.VT = o.tv * o.tile_v; s.border = shared ? 1 : 0;
+  return s;
 }
 
 int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st) {
-  int rc = stage_operand(q, p.n, p.H, p.W, p.q, (__nv_bfloat16*)(ws + p.off_qbf), (float*)(ws + p.off_q32),
-                         (float*)(ws + p.off_qss), (float*)(ws + p.off_rq), nullptr, st);
-  if (rc) return rc;
-  return stage_operand(k, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
-                       (float*)(ws + p.off_kss), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad), st);
+  const StageOp oq = make_op(q, p.n, p.H, p.W, p.q, (__nv_bfloat16*)(ws + p.off_qbf), (float*)(ws + p.off_q32),
+                             (float*)(ws + p.off_qss), (float*)(ws + p.off_rq), nullptr);
+  const StageOp ok = make_op(k, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
+                             (float*)(ws + p.off_kss), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad));
+  if ((long long)oq.nimg + ok.nimg > 65535) { set_error("stage_norm: too many images"); return SPEI_ERR_ARG; }
+  const int maxper = oq.Upad * oq.Vpad > ok.Upad * ok.Vpad ? oq.Upad * oq.Vpad : ok.Upad * ok.Vpad;
+  zero_padding_kernel<<<dim3((maxper + 255) / 256, 64, 2), 256, 0, st>>>(oq, ok);
+  SPEI_CUDA(cudaGetLastError());
+  const int maxW = oq.W > ok.W ? oq.W : ok.W, maxH = oq.H > ok.H ? oq.H : ok.H;
+  stage_transpose_kernel<<<dim3((maxW + kPx - 1) / kPx, maxH, oq.nimg + ok.nimg), 256, 0, st>>>(oq, ok);
+  SPEI_CUDA(cudaGetLastError());
+  const size_t tot = (size_t)oq.nimg * oq.H * oq.W + (size_t)ok.nimg * ok.H * ok.W + (size_t)ok.nimg * ok.UT * ok.VT;
+  patch_norms_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(oq, ok);
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
 }
 
 }  // namespace spei
