@@ -3,7 +3,7 @@
 //
 //  rescore_kernel       one warp per query: merges the per-segment top-k candidate lists of the bf16
 //                       pass, keeps those within eps of the best bf16 score, recomputes their relevance
-//                       exactly (fp32 operands, fp64 accumulation, 1152 terms) and picks the maximum with
+//                       exactly (fp32 operands, 4-term fp32 partial dots accumulated in fp64) and picks the maximum with
 //                       torch.max's first-index tie-break.  A query whose candidate list is saturated
 //                       (its k-th candidate is still inside the eps window, so a better key might have
 //                       been dropped) is queued for the exhaustive search below.
@@ -161,20 +161,27 @@ rescore_kernel(const RescoreParams p) {
       const float vbb = __shfl_sync(0xffffffffu, vb, src);
       const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
       const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // four independent chains (latency), fixed order
+      // Each lane owns 4 channels of every tap: their 4 products are summed in fp32 (one rounding of ~6e-8 relative per
+      // product, ~2e-9 absolute on a normalised score -- four orders of magnitude inside the 1e-5 near-tie rule) and the 9
+      // tap partials, then the 32 lanes, are accumulated in fp64.  The all-fp64 version (8 F2F + 4 DFMA per lane and tap)
+      // kept the conversion pipe 40 % busy (ncu, round 1) and was the kernel's top pipe.
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // three independent chains (taps t % 3), fixed order
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
         if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
           const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
           const float4 qq = qv[t * 32];
-          acc0 = fma((double)qq.x, (double)kv.x, acc0);
-          acc1 = fma((double)qq.y, (double)kv.y, acc1);
-          acc2 = fma((double)qq.z, (double)kv.z, acc2);
-          acc3 = fma((double)qq.w, (double)kv.w, acc3);
+          float part = qq.x * kv.x;
+          part = fmaf(qq.y, kv.y, part);
+          part = fmaf(qq.z, kv.z, part);
+          part = fmaf(qq.w, kv.w, part);
+          if (t % 3 == 0) acc0 += (double)part;
+          else if (t % 3 == 1) acc1 += (double)part;
+          else acc2 += (double)part;
         }
       }
-      double acc = (acc0 + acc1) + (acc2 + acc3);
+      double acc = (acc0 + acc1) + acc2;
 #pragma unroll
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);

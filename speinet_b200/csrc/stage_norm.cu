@@ -129,19 +129,29 @@ patch_norms_kernel(const StageOp oq, const StageOp ok) {
 }
 
 // Zeroes only what stage_transpose_kernel does not write: the 1-position border and the tile padding of the
-// [Vpad][Upad] planes of both operands (3-5 % of the buffers; a full cudaMemset cost ~10 us per call at 720p).
-// grid: (ceil(max plane / 256), 64 plane slices, 2 operands)
+// [Vpad][Upad] planes of both operands (1-5 % of the buffers; a full cudaMemset cost ~10 us per call at 720p).
+// Threads enumerate the padding positions only: first the full rows v = 0 and v > V, then the columns u = 0 and u > U
+// of the interior rows.   grid: (ceil(max padding positions / 256), 1, 2 operands)
 __global__ void __launch_bounds__(256)
 zero_padding_kernel(const StageOp oq, const StageOp ok) {
   const StageOp& o = blockIdx.z ? ok : oq;
-  const int per = o.Upad * o.Vpad;
+  const int full_rows = o.Vpad - o.V, side_cols = o.Upad - o.U;
+  const int n_full = full_rows * o.Upad, n_side = o.V * side_cols;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per) return;
-  const int v = i / o.Upad, u = i - v * o.Upad;
-  if (u >= 1 && u <= o.U && v >= 1 && v <= o.V) return;   // interior: written by the transpose kernel
+  if (i >= n_full + n_side) return;
+  int u, v;
+  if (i < n_full) {
+    const int row = i / o.Upad;
+    u = i - row * o.Upad;
+    v = row == 0 ? 0 : o.V + row;
+  } else {
+    const int j = i - n_full, row = j / side_cols, c = j - row * side_cols;
+    v = 1 + row;
+    u = c == 0 ? 0 : o.U + c;
+  }
+  const size_t per = (size_t)o.Upad * o.Vpad, pos = (size_t)v * o.Upad + u;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (int pl = blockIdx.y; pl < o.nimg * kCG; pl += gridDim.y)
-    *reinterpret_cast<uint4*>(o.bf + ((size_t)pl * per + i) * 8) = z;
+  for (int pl = 0; pl < o.nimg * kCG; ++pl) *reinterpret_cast<uint4*>(o.bf + (pl * per + pos) * 8) = z;
 }
 
 static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* r,
@@ -161,8 +171,8 @@ int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, c
   const StageOp ok = make_op(k, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
                              (float*)(ws + p.off_kss), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad));
   if ((long long)oq.nimg + ok.nimg > 65535) { set_error("stage_norm: too many images"); return SPEI_ERR_ARG; }
-  const int maxper = oq.Upad * oq.Vpad > ok.Upad * ok.Vpad ? oq.Upad * oq.Vpad : ok.Upad * ok.Vpad;
-  zero_padding_kernel<<<dim3((maxper + 255) / 256, 64, 2), 256, 0, st>>>(oq, ok);
+  const int padq = (oq.Vpad - oq.V) * oq.Upad + oq.V * (oq.Upad - oq.U), padk = (ok.Vpad - ok.V) * ok.Upad + ok.V * (ok.Upad - ok.U);
+  zero_padding_kernel<<<dim3(((padq > padk ? padq : padk) + 255) / 256, 1, 2), 256, 0, st>>>(oq, ok);
   SPEI_CUDA(cudaGetLastError());
   const int maxW = oq.W > ok.W ? oq.W : ok.W, maxH = oq.H > ok.H ? oq.H : ok.H;
   stage_transpose_kernel<<<dim3((maxW + kPx - 1) / kPx, maxH, oq.nimg + ok.nimg), 256, 0, st>>>(oq, ok);
