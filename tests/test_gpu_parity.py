@@ -308,6 +308,23 @@ def test_fusion_odd_sizes_vs_oracle():
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("hw", [(4, 4), (8, 8), (12, 11), (16, 40)])
+def test_fusion_small_and_partial_tiles_vs_oracle(hw):
+    """Planes smaller than / not a multiple of the 128-pixel tile on the TMA path (plane % 4 == 0): the tensor maps
+    clip the partial boxes of loads and stores.  (12, 11) at scale 1 has plane % 4 == 0; at scale 2 / 4 too."""
+    rng = np.random.default_rng(11)
+    h, w = hw
+    S = (rng.random((3, 1, h, w)) * 0.2).astype(np.float32)
+    for c, scale in ((128, 1), (64, 2), (32, 4)):
+        dec = rng.standard_normal((3, c, h * scale, w * scale)).astype(np.float32)
+        t = rng.standard_normal((3, c, h * scale, w * scale)).astype(np.float32)
+        wt = (rng.standard_normal((c, 2 * c, 1, 1)) * 0.05).astype(np.float32)
+        b = rng.standard_normal(c).astype(np.float32)
+        got = speinet_b200.fuse_level(cu(dec), cu(t), cu(S), cu(wt), cu(b), scale).cpu().numpy()
+        want = oracle.fuse_level(dec, t, S, wt, b, scale)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
 # ------------------------------------------------------------------ (f-3) Richardson-Lucy edge prior
 @pytest.mark.parametrize("name", ["uni", "img"])
 @pytest.mark.parametrize("iters", [1, 5])
