@@ -335,6 +335,17 @@ int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32
   return launch_rl_deconv(n, c, h, w, ks, num_iterations, regularization_strength, image, blur_kernel, out, (cudaStream_t)stream);
 }
 
+int spei_upsample2_bias_act(int32_t n, int32_t c, int32_t h, int32_t w, const float* y, const float* bias, int32_t relu, float* out,
+                            void* stream) {
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  if (n < 1 || c < 1 || h < 1 || w < 1) { set_error("bad upsample2_bias_act dims n=%d c=%d h=%d w=%d", n, c, h, w); return SPEI_ERR_ARG; }
+  if ((rc = check_ptr(y, "y", 4)) || (rc = check_ptr(out, "out", 8))) return rc;
+  if ((const void*)out == (const void*)y) { set_error("upsample2_bias_act: out must not alias y"); return SPEI_ERR_ARG; }
+  return launch_upsample2_bias_act(n, c, h, w, y, bias, relu, out, (cudaStream_t)stream);
+}
+
 int spei_search_transfer(const SpeiShape* shape, const float* q, const float* k, const float* ref1, const float* ref2,
                          const float* ref3, float* S, float* T3, float* T2, float* T1, int64_t* arg, int32_t* stats,
                          void* workspace, size_t workspace_bytes, void* stream) {

@@ -88,6 +88,8 @@ int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, c
 int launch_rl_deconv(int n, int c, int h, int w, int ks, int iters, float lambda, const float* img, const float* kern, float* out,
                      cudaStream_t st);
 
+int launch_upsample2_bias_act(int n, int c, int h, int w, const float* y, const float* bias, int relu, float* out, cudaStream_t st);
+
 // position <-> index helpers shared by kernels
 __host__ __device__ inline int uv_to_linear(int orient, int u, int v, int W) {
   return orient == 0 ? v * W + u : u * W + v;  // y*W + x

@@ -44,22 +44,47 @@ def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torc
     return out if out_dtype == torch.float32 else out.to(out_dtype)
 
 
+def up2_conv1x1_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, relu: bool = True) -> torch.Tensor:
+    """act(conv1x1(F.interpolate(x, scale_factor=2, mode='bicubic'); weight, bias)) without materialising the resized
+    input: the 1x1 convolution and the per-channel resize commute, so the channel mix runs at LOW resolution (one
+    library GEMM on a quarter of the pixels, fp32) and `spei_upsample2_bias_act` does resize + bias + ReLU in one pass.
+    Call sites in the reference: SearchTransfer.py:70-76 (SelfTransfer), speinet.py:99-100 and 111-112 (_decode)."""
+    lib = _lib.load()
+    out_dtype = x.dtype
+    xf = x.float().contiguous()
+    _check_inputs((xf,))
+    n, cin, h, w = xf.shape
+    wf = weight.detach().float().reshape(weight.shape[0], -1)
+    if wf.shape[1] != cin:
+        raise RuntimeError(f"up2_conv1x1_act: weight {tuple(weight.shape)} does not match {cin} input channels (1x1 kernels only)")
+    cout = wf.shape[0]
+    y = torch.matmul(wf, xf.view(n, cin, h * w)).view(n, cout, h, w).contiguous()     # W . x at low resolution
+    bf = bias.detach().float().contiguous() if bias is not None else None
+    with torch.cuda.device(xf.device):
+        out = torch.empty((n, cout, 2 * h, 2 * w), dtype=torch.float32, device=xf.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(xf.device).cuda_stream)
+        rc = lib.spei_upsample2_bias_act(n, cout, h, w, _ptr(y), _ptr(bf), 1 if relu else 0, _ptr(out), stream)
+        _lib.check(rc, "spei_upsample2_bias_act")
+    return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+
 def decode_fused(net, f_fusion, weight_S, sharp_lv3, sharp_lv2, sharp_lv1):
     """`SPEINet._decode` (speinet.py:92-120) with its three fusion lines routed through
-    `fuse_level`; everything else (decoders, search convs, bicubic resizes, outBlock) is the
-    reference's own PyTorch dataflow, reproduced op for op so outputs match."""
+    `fuse_level` and its two `relu(conv1x1(bicubic_x2(.)))` chains (:99-100, :111-112) through `up2_conv1x1_act`;
+    everything else (decoders, 3x3 search convs, the remaining resize, outBlock) is the reference's own PyTorch
+    dataflow, reproduced op for op so outputs match."""
     rn = net.recons_net
     up2 = lambda x: F.interpolate(x, scale_factor=2, mode="bicubic")
     f_lv3 = fuse_level(f_fusion, sharp_lv3, weight_S, net.conv_lv3.weight, net.conv_lv3.bias, 1)        # :93-94
     decoder_v2 = rn.decoder_second(f_lv3)                                                               # :95
     f_lv2 = fuse_level(decoder_v2, sharp_lv2, weight_S, net.conv_lv2.weight, net.conv_lv2.bias, 2)      # :96-97
-    s1 = F.relu(net.search1(up2(f_lv3)))                                                                # :99-100
+    s1 = up2_conv1x1_act(f_lv3, net.search1.weight, net.search1.bias)                                   # :99-100
     s2 = F.relu(net.search3(f_lv2))                                                                     # :101
     f_v3 = decoder_v2 + F.relu(net.search2(torch.cat((decoder_v2, s1), dim=1)))                         # :102,:104
     f_lv2 = f_lv2 + F.relu(net.search2(torch.cat((f_lv2, s2), dim=1)))                                  # :103,:105
     decoder_v1 = rn.decoder_first(f_lv2)                                                                # :107
     f_lv1 = fuse_level(decoder_v1, sharp_lv1, weight_S, net.conv_lv1.weight, net.conv_lv1.bias, 4)      # :108-109
-    s13 = F.relu(net.search13(up2(f_v3)))                                                               # :111-112
+    s13 = up2_conv1x1_act(f_v3, net.search13.weight, net.search13.bias)                                 # :111-112
     s23 = F.relu(net.search33(up2(f_lv2)))                                                              # :113-114
     s33 = F.relu(net.search43(f_lv1))                                                                   # :115
     pair = lambda a, b: F.relu(net.search33(torch.cat((a, b), dim=1)))                                  # :116-118

@@ -134,8 +134,8 @@ class SearchTransfer(nn.Module):
 
 class SelfTransfer(nn.Module):
     """Mirror of the reference SelfTransfer (SearchTransfer.py:53-79): the O(L^2) search runs in the
-    same kernels with keys = query transposed and flipped (:59) and no pyramid; the cheap
-    bicubic + 1x1-conv transfers (:70-76) stay PyTorch ops, as the scope table says."""
+    same kernels with keys = query transposed and flipped (:59) and no pyramid; the two
+    `relu(conv1x1(bicubic_x2(.)))` transfers (:70-76) run as a low-resolution GEMM + `spei_upsample2_bias_act`."""
 
     def __init__(self, n_feat: int = 32, search: str = "tcs", eps: float = 0.0):
         super().__init__()
@@ -146,6 +146,7 @@ class SelfTransfer(nn.Module):
     def forward(self, lrsr_lv3):
         keys = lrsr_lv3.transpose(2, 3).flip(2).contiguous()
         S, _, _, _, _, _ = search_transfer(lrsr_lv3, keys, search=self.search, eps=self.eps)
-        T_lv2 = F.relu(self.search1(F.interpolate(lrsr_lv3, scale_factor=2, mode="bicubic")))
-        T_lv1 = F.relu(self.search2(F.interpolate(T_lv2, scale_factor=2, mode="bicubic")))
+        from .fusion import up2_conv1x1_act   # resize + 1x1 conv + ReLU chains (:70-76) without the resized intermediates
+        T_lv2 = up2_conv1x1_act(lrsr_lv3, self.search1.weight, self.search1.bias)
+        T_lv1 = up2_conv1x1_act(T_lv2, self.search2.weight, self.search2.bias)
         return S, lrsr_lv3, T_lv2, T_lv1

@@ -325,6 +325,30 @@ def test_fusion_small_and_partial_tiles_vs_oracle(hw):
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
 
 
+# ------------------------------------------------------------------ (f-1 / f-3) resize + 1x1 conv + ReLU chains
+@pytest.mark.parametrize("dims", [(2, 128, 64, 9, 13), (1, 64, 32, 32, 48), (1, 128, 64, 5, 3)])
+def test_up2_conv1x1_relu_vs_reference_ops_and_oracle(dims):
+    """relu(conv1x1(F.interpolate(x, 2, bicubic))) (SearchTransfer.py:70-76, speinet.py:99-100,111-112): against the
+    numpy oracle in the reference's op order and against torch's own ops on the GPU (TF32 off)."""
+    import torch.nn.functional as F
+    n, cin, cout, h, w = dims
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, 1, 1)) * 0.1).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    got = speinet_b200.up2_conv1x1_act(cu(x), cu(wt), cu(b)).cpu().numpy()
+    up = oracle.bicubic_upsample(x, 2)
+    want = np.maximum(oracle.conv1x1(up, wt, b), 0)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = F.relu(F.conv2d(F.interpolate(cu(x), scale_factor=2, mode="bicubic"), cu(wt), cu(b))).cpu().numpy()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
 # ------------------------------------------------------------------ (f-3) Richardson-Lucy edge prior
 @pytest.mark.parametrize("name", ["uni", "img"])
 @pytest.mark.parametrize("iters", [1, 5])
