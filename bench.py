@@ -434,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
                      if args.search == "tcs" else "dense 9-tap implicit GEMM",
                      "dense_kernel": ({**dense, "frac": dense["achieved"] / peak_burst} if dense else None),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture under profiles/
-                     "traffic": 30.87e6 if args.search == "tcs" else 30.6e6, "traffic_source": "profiles/ ncu capture; algorithmic operand bytes 29.5e6"},
+                     "traffic": 30.58e6 if args.search == "tcs" else 30.6e6, "traffic_source": "profiles/ ncu capture; algorithmic operand bytes 29.5e6"},
         "e2e": {"value": world * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "repeats_s": [round(x, 5) for x in e2e_repeats], "timing": "median of 3 repeats (this rank; max over ranks of the medians)",
                 "max_abs_diff_vs_device_path": e2e_check,

@@ -325,6 +325,21 @@ def test_fusion_small_and_partial_tiles_vs_oracle(hw):
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
 
 
+def test_verify_window_repeats_with_the_rigorous_window():
+    """A deliberately tiny eps makes the measured bf16 deviation exceed 40 % of the window: verify_window=True must
+    notice (stats[2]) and fall back to the rigorous 2^-7 window; the result then agrees with the exhaustive fp32 search."""
+    rng = np.random.default_rng(31)
+    q = (rng.standard_normal((1, 128, 20, 28)) * 0.2).astype(np.float32)
+    k = (rng.standard_normal((1, 128, 20, 28)) * 0.04).astype(np.float32)
+    exact = speinet_b200.search_transfer(cu(q), cu(k), search="exact")
+    tiny = speinet_b200.search_transfer(cu(q), cu(k), eps=2e-5)
+    assert float(tiny[5][2].item()) * 1e-9 > 0.4 * 2e-5            # the window really was too tight for bf16
+    safe = speinet_b200.search_transfer(cu(q), cu(k), eps=2e-5, verify_window=True)
+    assert_indices_agree(q, [k], safe[4].cpu().numpy(), exact[4].cpu().numpy())
+    np.testing.assert_allclose(safe[0].cpu().numpy(), exact[0].cpu().numpy(), rtol=RTOL_S, atol=1e-6)
+    assert int(safe[5][1].item()) > int(tiny[5][1].item())        # more candidates were rescored in the second pass
+
+
 # ------------------------------------------------------------------ (f-1 / f-3) resize + 1x1 conv + ReLU chains
 @pytest.mark.parametrize("dims", [(2, 128, 64, 9, 13), (1, 64, 32, 32, 48), (1, 128, 64, 5, 3)])
 def test_up2_conv1x1_relu_vs_reference_ops_and_oracle(dims):
