@@ -103,95 +103,6 @@ gather_fold_slab_kernel(const int32_t* __restrict__ arg, const float* __restrict
   }
 }
 
-// Row-coalesced variant for the finest level.  ncu on the slab kernel above (random match field): DRAM reads are down to
-// one pass (118.8 MB) but l1tex throughput is 90 % of peak -- every 16-byte piece a thread reads lies in its own cache
-// line, so the L1 tag stage, one line per cycle, is the bound (66 M pieces per 720p launch).  A query's 12-pixel patch
-// row is 48 contiguous bytes that feed three neighbouring output cells; here THREE ADJACENT LANES read those 48 bytes
-// in one instruction (one tag lookup instead of three), park the pieces in shared memory under (neighbour, channel,
-// sub-row, cell), and a second phase adds each output's 9 pieces in col2im order.  Same adds, same order: bit-identical.
-//   load task = (query (Y+dy, qx), channel, sub-row), qx in [X0-1, X0+32]: piece j (source cell wr-1+j) goes to output
-//   cell qx-1+j as its neighbour (dy, dx = 1-j).  Every (cell, neighbour) slot is written exactly once per round (zero
-//   when there is no contribution), so the buffer needs no clearing.
-// grid: (ceil(W/32), H, n * C/8)   block 256; dynamic smem 9 x 8 ch x 2 sub-rows x 32 cells x 16 B = 73.7 KB, 2 rounds
-constexpr int kGrCells = 32, kGrCh = 8, kGrRows = 2, kGrQ = kGrCells + 2;
-template <bool kCpuOrder, bool kTrueDiv>
-__global__ void __launch_bounds__(256)
-gather_fold_rows_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
-                        int H, int W, int Hr, int Wr) {
-  constexpr int S = 4;
-  extern __shared__ float4 gr_smem[];                    // [9 t][kGrCh][kGrRows][kGrCells]
-  __shared__ long long s_src[3][kGrQ];                   // per (dy, query): float offset of (channel 0, source row cy*4, cell wr), or -1
-  __shared__ int s_wr[3][kGrQ];                          // source cell column wr of the query's match (for the range test of each piece)
-  const int X0 = blockIdx.x * kGrCells, Y = blockIdx.y;
-  const int slabs = C / kGrCh, n = blockIdx.z / slabs, c0 = (blockIdx.z - n * slabs) * kGrCh;
-  const int lk1 = Hr * Wr, jmax = rf * lk1 - 1;
-  const size_t ref_plane = (size_t)(S * Hr) * (S * Wr);
-  const int ref_pitch = S * Wr;
-  const int32_t* a = arg + (size_t)n * H * W;
-  for (int e = threadIdx.x; e < 3 * kGrQ; e += 256) {
-    const int d = e / kGrQ, qi = e - d * kGrQ;
-    const int qy = Y + d - 1, qx = X0 - 1 + qi;
-    long long o = -1;
-    int wr = 0;
-    if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
-      int j = __ldg(a + qy * W + qx);
-      j = min(max(j, 0), jmax);
-      const int f = j / lk1, rem = j - f * lk1;
-      const int hr = rem / Wr;
-      wr = rem - hr * Wr;
-      const int cy = Y + hr - qy;                        // source cell row (the same for the three target cells)
-      if (cy >= 0 && cy < Hr)
-        o = (long long)f * C * (long long)ref_plane + (long long)(cy * S) * ref_pitch + (long long)wr * S;
-    }
-    s_src[d][qi] = o;
-    s_wr[d][qi] = wr;
-  }
-  __syncthreads();
-  const float* rbase = ref + (size_t)n * rf * C * ref_plane + (size_t)c0 * ref_plane;
-  const size_t out_plane = (size_t)(S * H) * (S * W);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int piece = lane % 3, tslot = lane / 3;          // lanes 30, 31 idle in the load phase
-  constexpr int kTasks = 3 * kGrQ * kGrCh * kGrRows;     // per round: (dy, query, channel, sub-row)
-#pragma unroll 1
-  for (int round = 0; round < S / kGrRows; ++round) {
-    // ---- phase 1: coalesced 48-byte row reads -> shared memory ----
-    if (tslot < 10) {
-      for (int task = warp * 10 + tslot; task < kTasks; task += 80) {
-        const int qi = task % kGrQ, rest = task / kGrQ;
-        const int d = rest % 3, rest2 = rest / 3;
-        const int rr = rest2 % kGrRows, ch = rest2 / kGrRows;
-        const int cell = qi - 2 + piece;                 // target cell index in the block: (qx - 1 + piece) - X0
-        if (cell < 0 || cell >= kGrCells) continue;
-        const long long o = s_src[d][qi];
-        const int cx = s_wr[d][qi] - 1 + piece;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o >= 0 && cx >= 0 && cx < Wr)
-          v = __ldg(reinterpret_cast<const float4*>(rbase + o + (size_t)ch * ref_plane + (size_t)(round * kGrRows + rr) * ref_pitch) + (piece - 1));
-        const int dx = 1 - piece, tt = d * 3 + (dx + 1);  // neighbour (dy = d - 1, dx) of the target cell
-        const int t = kCpuOrder ? 8 - tt : tt;           // position in the summation order
-        gr_smem[((t * kGrCh + ch) * kGrRows + rr) * kGrCells + cell] = v;
-      }
-    }
-    __syncthreads();
-    // ---- phase 2: 9 pieces per output in col2im order, x 1/9, store ----
-    {
-      const int cell = lane, ch = warp;                  // 8 warps = 8 channels of the slab
-      const int X = X0 + cell;
-      if (X < W) {
-#pragma unroll
-        for (int rr = 0; rr < kGrRows; ++rr) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) vadd(acc, gr_smem[((t * kGrCh + ch) * kGrRows + rr) * kGrCells + cell]);
-          float* dst = out + ((size_t)n * C + c0 + ch) * out_plane + (size_t)(Y * S + round * kGrRows + rr) * (S * W) + (size_t)X * S;
-          __stcs(reinterpret_cast<float4*>(dst), fin<kTrueDiv>(acc));
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // grid: (ceil(W/32), S*H, n)   block: (32 cells, 8 channel lanes)
 template <int S, bool kCpuOrder, bool kTrueDiv>
 __global__ void __launch_bounds__(256)
@@ -269,21 +180,8 @@ int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int s
     else { if (true_div) GF(S_, false, true); else GF(S_, false, false); }          \
   } while (0)
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
-  static const bool no_slab = getenv("SPEI_GATHER_NO_SLAB") != nullptr;  // A/B switches
-  static const bool no_rows = getenv("SPEI_GATHER_NO_ROWS") != nullptr;
-  if (scale == 4 && !no_rows && !no_slab && (long long)n * (c / 8) <= 65535 && wr >= 1) {
-    const dim3 rgrid((w + kGrCells - 1) / kGrCells, h, n * (c / 8));
-    const int smem = 9 * kGrCh * kGrRows * kGrCells * (int)sizeof(float4);
-#define GFR(O_, D_)                                                                                                     \
-  do {                                                                                                                  \
-    SPEI_CUDA(cudaFuncSetAttribute(gather_fold_rows_kernel<O_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    gather_fold_rows_kernel<O_, D_><<<rgrid, 256, smem, st>>>(arg32, ref, out, rf, c, h, w, hr, wr);                  \
-  } while (0)
-    if (cpu_order) { if (true_div) GFR(true, true); else GFR(true, false); }
-    else { if (true_div) GFR(false, true); else GFR(false, false); }
-#undef GFR
-  }
-  else if (scale == 4 && !no_slab && (long long)n * (c / 8) <= 65535) {
+  static const bool no_slab = getenv("SPEI_GATHER_NO_SLAB") != nullptr;  // A/B switch
+  if (scale == 4 && !no_slab && (long long)n * (c / 8) <= 65535) {
     const dim3 sgrid((w + 31) / 32, h, n * (c / 8));
 #define GFL(O_, D_) gather_fold_slab_kernel<4, O_, D_><<<sgrid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
     if (cpu_order) { if (true_div) GFL(true, true); else GFL(true, false); }
