@@ -158,6 +158,35 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
     return 1.0 / frame_s, info, t_step
 
 
+def stock_pytorch_gpu_reference(dev, d, convs):
+    """oracle/torch_port.py (the reference's ATen sequence: unfold, normalize, bmm, max, gather x3, fold x3, /9, then the three
+    fusion lines) on CUDA tensors of this GPU, fp32, timed with CUDA events.  Part of the baseline leg only."""
+    from oracle import torch_port as tp
+    try:
+        def frame():
+            S, T3, T2, T1, _ = tp.search_transfer_torch(d["q"], d["lv3"], d["lv1"], d["lv2"], d["lv3"])
+            outs = []
+            for lvl, T, dec, sc in ((3, T3, d["dec3"], 1), (2, T2, d["dec2"], 2), (1, T1, d["dec1"], 4)):
+                outs.append(tp.fuse_level_torch(dec, T, S, convs[lvl].weight.detach(), convs[lvl].bias.detach(), sc))
+            return outs
+        frame()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            frame()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / 2
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        torch.cuda.empty_cache()
+        return {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "peak_memory_GB": round(peak_gb, 1),
+                "note": "torch 2.11 eager, cuBLAS sgemm (TF32 off, as in the inference script), R = 13.27 GB materialised"}
+    except Exception as e:  # noqa: BLE001  (e.g. out of memory on a shared device)
+        torch.cuda.empty_cache()
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -449,6 +478,9 @@ def run_ours(args, rank, world, local_rank):
         fps, info, _ = cpu_reference_run(steps=4, warmup=1, budget_s=25.0)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                                 "detail": {k: v for k, v in info.items() if k != "sample"}}
+        # still the baseline leg: the same reference op sequence in STOCK PyTorch on this GPU (SURVEY.md section 8(d):
+        # "that, not the CPU, is the meaningful before").  Full 720p size, whole frame, 1 warm-up + 2 timed calls.
+        line["cpu_baseline"]["detail"]["reference_ops_stock_pytorch_on_this_gpu"] = stock_pytorch_gpu_reference(dev, d, convs)
     print(json.dumps(line), flush=True)
 
 
