@@ -93,6 +93,26 @@ def test_tc_search_matches_oracle_random(shape, search):
 
 
 @pytest.mark.parametrize("search", TC_MODES)
+def test_tc_search_random_shape_sweep_vs_exhaustive_fp32(search):
+    """24 seeded random problem shapes (batch 1-3, 1-3 reference frames, grids from 1x1 to ~100x150, query and reference
+    grids unrelated) through both tcgen05 engines against the exhaustive fp32 search on the same GPU: every persistent-CTA
+    split, tile-padding and barrier-phase pattern the planner can produce at these sizes."""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        n, rf = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        h, w, hr, wr = (int(rng.integers(1, hi)) for hi in ((20, 40, 20, 40) if case % 3 else (100, 150, 100, 150)))
+        q = torch.from_numpy((rng.standard_normal((n, 128, h, w)) * 0.2).astype(np.float32)).cuda()
+        k = torch.from_numpy((rng.standard_normal((n, rf, 128, hr, wr)) * 0.04).astype(np.float32)).cuda()
+        S0, a0, _, f0 = U.run_search(q, k, search=_lib.SEARCH_EXACT)
+        S1, a1, st1, f1 = U.run_search(q, k, search=SEARCH_MODES[search])
+        assert f0 == 0 and f1 == 0, (case, n, rf, h, w, hr, wr)
+        diff = (a0 != a1)
+        if diff.any():   # differing indices must be near-ties: compare the exact scores both engines report
+            assert float((S0.reshape(n, -1)[diff] - S1.reshape(n, -1)[diff]).abs().max()) < 1e-5, (case, n, rf, h, w, hr, wr)
+        torch.testing.assert_close(S1, S0, rtol=RTOL_S, atol=1e-6, msg=lambda m: f"case {case} {(n, rf, h, w, hr, wr)}: {m}")
+
+
+@pytest.mark.parametrize("search", TC_MODES)
 def test_tc_search_smooth_features_many_near_candidates(search):
     """Image-like (spatially smooth) features put many keys inside the candidate window; the
     saturated-list -> exhaustive fp32 fallback must keep the result exact."""
@@ -201,6 +221,42 @@ def test_module_vs_torch_cuda_reference_ops_medium():
     same = (arg == warg)
     if bool(same.all()):
         assert torch.equal(T3, w3) and torch.equal(T2, w2) and torch.equal(T1, w1)
+
+
+def test_module_random_shape_sweep_vs_torch_cuda_ops():
+    """12 seeded random shapes (query and reference grids unrelated, batch 1-3) through the drop-in module against the
+    reference's ATen sequence on the same GPU: S within 1e-4, and wherever the argmax indices are identical the three
+    transferred pyramids must be BIT-identical (torch-CUDA col2im order, x * (1/9f))."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(77)
+    st = speinet_b200.SearchTransfer().cuda()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for case in range(12):
+            n = int(rng.integers(1, 4))
+            h, w, hr, wr = (int(rng.integers(1, hi)) for hi in (24, 36, 24, 36))
+            mk = lambda *shape, std: torch.from_numpy((rng.standard_normal(shape) * std).astype(np.float32)).cuda()
+            q, lv3 = mk(n, 128, h, w, std=0.2), mk(n, 128, hr, wr, std=0.04)
+            lv2, lv1 = mk(n, 64, 2 * hr, 2 * wr, std=0.04), mk(n, 32, 4 * hr, 4 * wr, std=0.04)
+            # reference ops with a reference grid that differs from the query grid (fold sizes follow the QUERY, :44-46)
+            keys = F.normalize(F.unfold(lv3, 3, padding=1).permute(0, 2, 1), dim=2)
+            r_star, r_arg = torch.max(torch.bmm(keys, F.normalize(F.unfold(q, 3, padding=1), dim=1)), dim=1)
+            want = {}
+            for lvl, ref, p in ((3, lv3, dict(kernel_size=3, padding=1, stride=1)), (2, lv2, dict(kernel_size=6, padding=2, stride=2)),
+                                (1, lv1, dict(kernel_size=12, padding=4, stride=4))):
+                cols = F.unfold(ref, **p)
+                picked = torch.gather(cols, 2, r_arg[:, None, :].expand(-1, cols.size(1), -1))
+                want[lvl] = F.fold(picked, output_size=(h * p["stride"], w * p["stride"]), **p) / (3. * 3.)
+            with torch.no_grad():
+                S, T3, T2, T1, arg = st(q, lv3, lv1, lv2, lv3, return_index=True)
+            tag = f"case {case} {(n, h, w, hr, wr)}"
+            torch.testing.assert_close(S.reshape(n, -1), r_star, rtol=RTOL_S, atol=1e-6, msg=lambda m: f"{tag}: {m}")
+            assert_indices_agree(q.cpu().numpy(), lv3.cpu().numpy(), arg.cpu().numpy(), r_arg.cpu().numpy())
+            if bool((arg == r_arg).all()):
+                assert torch.equal(T3, want[3]) and torch.equal(T2, want[2]) and torch.equal(T1, want[1]), tag
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def search_transfer_torch_cuda(q, lv3, lv1, lv2, ref3):
