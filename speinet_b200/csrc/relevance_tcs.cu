@@ -45,6 +45,10 @@
 
 namespace spei {
 
+#ifndef SPEI_TCS_STAGES
+#define SPEI_TCS_STAGES 6
+#endif
+constexpr int kSStages = SPEI_TCS_STAGES;   // key pipeline depth (4 stages = one key tile)
 constexpr int kSThreads = 384;
 constexpr uint32_t kSRowBytes = kSBoxU * 16;                                  // 512 B
 constexpr uint32_t kSSBO = 128;                                               // 8 positions x 16 B
@@ -53,8 +57,8 @@ constexpr uint32_t kSQLBO = kSQRows * kSRowBytes;                             //
 constexpr uint32_t kSQTileBytes = kCG * kSQLBO;                               // 49152
 constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       // 20480
 constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
-constexpr uint32_t kSNumBars = 2 * kStages + 6;
-constexpr uint32_t kSRkOffset = kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
+constexpr uint32_t kSNumBars = 2 * kSStages + 6;
+constexpr uint32_t kSRkOffset = kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
 constexpr uint32_t kSRkWarpFloats = 132;  // [<=4 rows][32] reciprocal key norms + 4 row maxima
 constexpr uint32_t kSSmemBytes = kSRkOffset + 8 * kSRkWarpFloats * 4;
 static_assert(kSRkOffset % 16 == 0, "key-norm staging must be float4 aligned");
@@ -98,18 +102,18 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + kSQTileBytes;
-  const uint32_t bars = sK + kStages * kSStageBytesMax;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages;
-  const uint32_t bar_qfull = bars + 16 * kStages, bar_qfree = bar_qfull + 8;
+  const uint32_t bars = sK + kSStages * kSStageBytesMax;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kSStages;
+  const uint32_t bar_qfull = bars + 16 * kSStages, bar_qfree = bar_qfull + 8;
   const uint32_t bar_tfull = bar_qfull + 16, bar_tempty = bar_qfull + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSQTileBytes + kStages * kSStageBytesMax + kSNumBars * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
   const long long pb = (long long)b * p.P / p.G, pe = (long long)(b + 1) * p.P / p.G;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kSStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_qfull, 1); mbar_init(bar_qfree, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,7 +152,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes);
           tma_load_4d(sK + stage * kSStageBytesMax, &tmk, bar_full + 8 * stage, ktu * kSTileU * 8, ktv * p.Ny, (int)(s4 * kCGS),
                       ix.item * p.rf + f);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -190,7 +194,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
             }
           }
           tc_commit(bar_empty + 8 * stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSStages) { stage = 0; phase ^= 1; }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (ix.kt == p.KT - 1 && pp + 1 < pe) tc_commit(bar_qfree);
