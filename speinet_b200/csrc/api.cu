@@ -63,7 +63,7 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   Plan p{};
   const bool shared = s.search == SPEI_SEARCH_TCS;
   p.mode = shared ? SPEI_SEARCH_TCS : SPEI_SEARCH_TC;
-  p.nlist = shared ? 2 : 1;
+  p.nlist = shared ? tcs_epilogue_groups() : 1;
   p.n = s.n; p.rf = s.rf; p.H = s.h; p.W = s.w; p.Hr = s.hr; p.Wr = s.wr;
   if (!shared) {
     // the MMA applies all nine taps with per-operand address offsets: each operand picks its own orientation

@@ -49,7 +49,13 @@ namespace spei {
 #define SPEI_TCS_STAGES 6
 #endif
 constexpr int kSStages = SPEI_TCS_STAGES;   // key pipeline depth (4 stages = one key tile)
-constexpr int kSThreads = 384;
+#ifndef SPEI_TCS_GROUPS
+#define SPEI_TCS_GROUPS 2
+#endif
+constexpr int kSGroups = SPEI_TCS_GROUPS;     // epilogue warp groups (4 warps each); group g drains key rows [g*Ny/G, ...)
+constexpr int kSThreads = (4 + 4 * kSGroups) * 32;
+// register budget per thread after setmaxnreg: 4 non-epilogue warps shrink to 48, the epilogue warps share the rest
+constexpr int kSEpiRegs = ((65536 - 4 * 32 * 48) / (4 * kSGroups * 32)) / 8 * 8 > 232 ? 232 : ((65536 - 4 * 32 * 48) / (4 * kSGroups * 32)) / 8 * 8;
 constexpr uint32_t kSRowBytes = kSBoxU * 16;                                  // 512 B
 constexpr uint32_t kSSBO = 128;                                               // 8 positions x 16 B
 constexpr uint32_t kSQRows = kSQTileV + 2;                                    // 6
@@ -58,9 +64,9 @@ constexpr uint32_t kSQTileBytes = kCG * kSQLBO;                               //
 constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       // 20480
 constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
 constexpr uint32_t kSNumBars = 2 * kSStages + 6;
-constexpr uint32_t kSRkOffset = kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8 + 16;  // 8 warps x 128 floats
+constexpr uint32_t kSRkOffset = kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8 + 16;  // per epilogue warp: 128 floats + row maxima
 constexpr uint32_t kSRkWarpFloats = 132;  // [<=4 rows][32] reciprocal key norms + 4 row maxima
-constexpr uint32_t kSSmemBytes = kSRkOffset + 8 * kSRkWarpFloats * 4;
+constexpr uint32_t kSSmemBytes = kSRkOffset + 4 * kSGroups * kSRkWarpFloats * 4;
 static_assert(kSRkOffset % 16 == 0, "key-norm staging must be float4 aligned");
 constexpr uint32_t kSTmemCols = 512;
 constexpr uint32_t kSAccCols = 256;
@@ -115,7 +121,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kSStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_qfull, 1); mbar_init(bar_qfree, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4 * kSGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmq) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmk) : "memory");
@@ -128,7 +134,11 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  // register re-balancing (one warpgroup = 4 consecutive warps): the producer / issuer / allocator warps need few
+  // registers, the epilogue warps hold a top-k list, two TMEM loads and a row of tap sums each
+  // (each setmaxnreg sits at the top of the branch it governs, so the compiler's budget for that branch is unambiguous)
+  if (warp < 4) {
+    if (kSGroups >= 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
@@ -203,13 +213,17 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (b == 3) printf("mma: total %lld wait_tempty %lld wait_full %lld tiles %lld\n", clock64() - pt0, p_tempty, p_full, pe - pb);
 #endif
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ======================================= epilogue =======================================
+    if (kSGroups >= 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSEpiRegs));
     const int ew = (warp - 4) & 3;        // TMEM lane quarter this warp may read (= warp % 4) = tile row v
-    const int half = (warp - 4) >> 2;     // which half of a tile's key rows
+    const int half = (warp - 4) >> 2;     // epilogue group: which share of a tile's key rows
     const int m = ew * 32 + lane;         // MMA row: query (qu = lane, qv = ew) of the tile
     const int qu = lane, qv = ew;
-    const int r_lo = half == 0 ? 0 : (p.Ny + 1) / 2, r_hi = half == 0 ? (p.Ny + 1) / 2 : p.Ny;
+    // rows split as evenly as possible, the larger shares first: Ny = 8, 3 groups -> 3 / 3 / 2
+    const int r_base = p.Ny / kSGroups, r_rem = p.Ny % kSGroups;
+    const int r_lo = half * r_base + (half < r_rem ? half : r_rem), r_hi = r_lo + r_base + (half < r_rem ? 1 : 0);
     float tv[kTopK];
     int ti[kTopK];
     uint32_t tile_i = 0;
@@ -422,9 +436,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (pp + 1 == pe || ix.kt == p.KT - 1) {
         if (qlin >= 0) {
           const long long p0 = ((long long)ix.item * p.QT + ix.qt) * p.KT;
-          const int slot = (b - (int)(((p0 + 1) * (long long)p.G - 1) / p.P)) * 2 + half;
-          float4* dv = reinterpret_cast<float4*>(p.cval + ((size_t)qlin * p.maxseg * 2 + slot) * kTopK);
-          int4* di = reinterpret_cast<int4*>(p.cidx + ((size_t)qlin * p.maxseg * 2 + slot) * kTopK);
+          const int slot = (b - (int)(((p0 + 1) * (long long)p.G - 1) / p.P)) * kSGroups + half;
+          float4* dv = reinterpret_cast<float4*>(p.cval + ((size_t)qlin * p.maxseg * kSGroups + slot) * kTopK);
+          int4* di = reinterpret_cast<int4*>(p.cidx + ((size_t)qlin * p.maxseg * kSGroups + slot) * kTopK);
 #pragma unroll
           for (int s4 = 0; s4 < kTopK / 4; ++s4) {
             dv[s4] = make_float4(tv[4 * s4], tv[4 * s4 + 1], tv[4 * s4 + 2], tv[4 * s4 + 3]);
@@ -462,6 +476,8 @@ static int make_map_s(EncodeTiledFn enc, CUtensorMap* tm, void* base, int nimg, 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
   return SPEI_OK;
 }
+
+int tcs_epilogue_groups() { return kSGroups; }
 
 int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   EncodeTiledFn enc;

@@ -73,6 +73,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st);
 int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st);
 int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st);
+int tcs_epilogue_groups();   // candidate lists per (query, key segment) the tap-sharing kernel writes
 void set_debug_acc(float* ptr);
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st);
