@@ -277,14 +277,25 @@ def run_ours(args, rank, world, local_rank):
             c = T[lvl].shape[1]
             chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
                                     vp(Fo[lvl]), st_handle), "fuse_level")
-        if world > 1:  # gather a frame-shaped output across ranks (the path's only collective)
-            dist.all_gather_into_tensor(frame_out, Fo[1][:, :3].contiguous())
+        if world > 1:
+            # gather a frame-shaped output across ranks (the path's only collective).  Asynchronous: NCCL's stream waits
+            # for this clip's kernels, the compute stream does not wait for NCCL, so the 11 MB x world gather overlaps the
+            # next clip's search; every handle is waited for before the timed region closes.
+            gather_work.append(dist.all_gather_into_tensor(frame_out, Fo[1][:, :3].contiguous(), async_op=True))
+
+    gather_work = []
+
+    def finish_gathers():
+        for wk in gather_work:
+            wk.wait()
+        gather_work.clear()
 
     def run_steps(count, events=None):
         if not args.overlap:
             for i in range(count):
                 search_part(i, stream, events[i] if events else None)
                 transfer_part(i, stream)
+            finish_gathers()
             return
         main = torch.cuda.current_stream(dev)
         fork = torch.cuda.Event()
@@ -305,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
                 done_b[i].record(sB)
         main.wait_stream(sA)
         main.wait_stream(sB)
+        finish_gathers()
 
     def barrier():
         if world > 1:
