@@ -17,4 +17,7 @@ try:
 except Exception as e: print('parse failed', e)
 PY
 done
-[ -n "$SKIP_REF" ] || timeout 600 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err&& { echo "reference arm exit $?"; tail -c 600 gpurun_out/bench_ref_n1.json; }
+if [ -z "$SKIP_REF" ]; then
+  timeout 600 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_n1.err
+  echo "reference arm exit $?"; tail -c 600 gpurun_out/bench_ref_n1.json
+fi
