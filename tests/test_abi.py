@@ -67,3 +67,23 @@ def test_no_silent_fallback_without_gpu(lib):
     ok = _lib.SpeiShape(n=1, h=8, w=8, hr=8, wr=8, rf=1, c3=128, c2=64, c1=32)
     n = ctypes.c_size_t(0)
     assert lib.spei_workspace_bytes(ctypes.byref(ok), ctypes.byref(n)) < 0
+    # the stand-alone entry points check the device before anything else: no GPU -> error code + message, never a result
+    null = ctypes.c_void_p(0)
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.spei_fuse_level(1, 32, 4, 4, 1, p, p, p, p, p, p, null) < 0 and lib.spei_last_error()
+    assert lib.spei_rl_deconv(1, 1, 4, 4, 5, 1, ctypes.c_float(0.01), p, p, p, null) < 0 and lib.spei_last_error()
+    assert lib.spei_upsample2_bias_act(1, 1, 4, 4, p, p, 1, p, null) < 0 and lib.spei_last_error()
+
+
+def test_python_modules_refuse_cpu_tensors():
+    """The public wrappers of the rows next to the path (edge prior, resize + conv chains) have no CPU path either."""
+    import torch
+    import speinet_b200
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        speinet_b200.r_l_per_channel(x, speinet_b200.create_blur_kernel(), 1, 0.01)
+    with pytest.raises(RuntimeError):
+        speinet_b200.up2_conv1x1_act(torch.rand(1, 8, 4, 4), torch.rand(4, 8, 1, 1), torch.rand(4))
+    assert tuple(speinet_b200.create_blur_kernel().shape) == (1, 1, 5, 5)
+    assert abs(float(speinet_b200.create_blur_kernel().sum()) - 1.0) < 1e-6     # rcl.py:18-20

@@ -170,3 +170,15 @@ def test_rl_deconv_semantics_zero_and_negative():
     neg = -x
     out_neg = oracle.r_l_per_channel(neg, oracle.create_blur_kernel(), 1, 0.01)  # x/blurred > 0 for an all-negative frame
     assert np.isfinite(out_neg).all()
+
+
+def test_conv1x1_commutes_with_bicubic_resize():
+    """The identity `up2_conv1x1_act` relies on: relu(conv1x1(up2(x)) + b) == relu(up2(W . x) + b) (both maps are linear,
+    one mixes channels per pixel, the other pixels per channel; the border-clamped bicubic taps sum to 1)."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 16, 7, 9)).astype(np.float32)
+    w = (rng.standard_normal((8, 16, 1, 1)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(8).astype(np.float32)
+    ref_order = np.maximum(oracle.conv1x1(oracle.bicubic_upsample(x, 2), w, b), 0)          # SearchTransfer.py:70-72 order
+    low_res_first = np.maximum(oracle.bicubic_upsample(oracle.conv1x1(x, w, np.zeros(8, np.float32)), 2) + b[None, :, None, None], 0)
+    np.testing.assert_allclose(low_res_first, ref_order, rtol=1e-4, atol=1e-5)
