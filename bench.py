@@ -268,15 +268,41 @@ def run_ours(args, rank, world, local_rank):
         if ev:
             ev[1].record(torch.cuda.current_stream(dev))
 
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(2)] if args.lanes else []
+
+    def level_chain(lvl, w, st_handle):
+        c = T[lvl].shape[1]
+        chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), vp(k5), w, nbytes.value, st_handle), "gather_fold")
+        chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
+                                vp(Fo[lvl]), st_handle), "fuse_level")
+
     def transfer_part(i, st_handle):
         w = wsps[i & 1]
         chk(lib.spei_rescore(sref, vp(S), vp(arg32), ctypes.c_void_p(0), vp(stats), w, nbytes.value, st_handle), "rescore")
-        for lvl in (3, 2, 1):
-            chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), vp(k5), w, nbytes.value, st_handle), "gather_fold")
-        for lvl in (3, 2, 1):
-            c = T[lvl].shape[1]
-            chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
-                                    vp(Fo[lvl]), st_handle), "fuse_level")
+        if args.lanes:
+            # the three pyramid levels are independent after the rescoring: lv1 stays on the main stream, lv2 and lv3
+            # run their gather -> fusion chains on two side streams (fork / join with events)
+            cur = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            joins = []
+            for ls, lvl in zip(lane_streams, (2, 3)):
+                ls.wait_event(fork)
+                with torch.cuda.stream(ls):
+                    level_chain(lvl, w, ctypes.c_void_p(ls.cuda_stream))
+                    ev = torch.cuda.Event()
+                    ev.record(ls)
+                    joins.append(ev)
+            level_chain(1, w, st_handle)
+            for ev in joins:
+                cur.wait_event(ev)
+        else:
+            for lvl in (3, 2, 1):
+                chk(lib.spei_gather_fold(sref, lvl, vp(arg32), vp(refs[lvl]), vp(T[lvl]), vp(k5), w, nbytes.value, st_handle), "gather_fold")
+            for lvl in (3, 2, 1):
+                c = T[lvl].shape[1]
+                chk(lib.spei_fuse_level(1, c, H, W, scale[lvl], vp(decs[lvl]), vp(T[lvl]), vp(S), vp(wts[lvl][0]), vp(wts[lvl][1]),
+                                        vp(Fo[lvl]), st_handle), "fuse_level")
         if world > 1:
             # gather a frame-shaped output across ranks (the path's only collective).  Asynchronous: NCCL's stream waits
             # for this clip's kernels, the compute stream does not wait for NCCL, so the 11 MB x world gather overlaps the
@@ -506,6 +532,7 @@ def main():
     ap.add_argument("--search", default="tcs", choices=["tc", "tcs"], help="tcgen05 candidate pass: dense 9-tap MMA or tap-sharing")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs only; not a valid bench line)")
     ap.add_argument("--overlap", action="store_true", help="two-stream pipeline across consecutive clips (see run_ours)")
+    ap.add_argument("--lanes", action="store_true", help="experiment: run the three gather -> fusion chains of a clip on parallel streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
