@@ -666,3 +666,11 @@ def test_row_sharded_frame_equals_unsharded(world):
     for i in range(4):
         stitched = torch.cat([b[i] for b in bands], dim=2)
         assert torch.equal(stitched, full[i]), f"output {i} differs between row-sharded and unsharded"
+
+
+def test_integration_md_ctypes_stub_matches_module():
+    """The minimal ctypes binding printed in INTEGRATION.md section 3, executed verbatim, against the drop-in module."""
+    import os
+    import runpy
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, "tools", "check_integration_stub.py"), run_name="__main__")
