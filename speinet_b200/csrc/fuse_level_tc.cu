@@ -4,6 +4,14 @@
 //     out = dec + (W . cat(dec, T) + b) * bicubic_up(S, scale)
 //
 // as ONE pass over HBM (read dec, read T, write out = 3 x tensor size, the algorithmic minimum).
+//
+// Three tcgen05 kernels live in this file (DESIGN.md section 4(d) has the measurements that led from one to the next):
+//   fuse_level_ts_kernel   DEFAULT.  Activations = A operand from tensor memory, resident weight tiles, TMA-fed residual
+//                          and TMA-store epilogue.                                    (second half of the file)
+//   fuse_level_tma_kernel  both operands in shared memory, TMA-fed; kept for A/B (SPEI_FUSE_SS=1).
+//   fuse_level_tc_kernel   LDG-fed, no alignment requirement: the path for planes whose byte stride is not a multiple of
+//                          16 (TMA needs that), described next.
+//
 // The 1x1 convolution is a skinny GEMM  D[pixel, o] = sum_k X[k, pixel] * W[o, k]  (K = 2C) that must keep
 // fp32 accuracy (1e-4 bar), so it runs as 3xTF32 on tcgen05: x = hi + lo with hi = x truncated to TF32 and
 // lo = x - hi (exact), D ~= Xlo.Whi + Xhi.Wlo + Xhi.Whi with fp32 accumulation in TMEM (dropped term
