@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPEI_VERSION 100
+#define SPEI_VERSION 200
 
 #define SPEI_OK 0
 #define SPEI_ERR_ARG (-1)        /* NULL pointer / bad shape / misaligned pointer            */
@@ -41,12 +41,12 @@ extern "C" {
 #define SPEI_FOLD_CPU 3       /* what torch does on the CPU: CPU col2im order, x/9             */
 
 /* relevance engine */
-#define SPEI_SEARCH_TC 0    /* tcgen05 bf16 candidate pass + exact fp32 rescoring (default)  */
+#define SPEI_SEARCH_TC 0    /* tcgen05 bf16 candidate pass, dense 9-tap implicit GEMM, + exact fp32 rescoring */
 #define SPEI_SEARCH_EXACT 1 /* fp32 CUDA-core exhaustive search (checker / debugging)        */
 #define SPEI_SEARCH_TCS 2   /* tcgen05 bf16 candidate pass with tap sharing: the MMA contracts channels x the 3 taps
                                along one image axis (K = 384), the epilogue adds the 3 taps along the other axis from
                                neighbouring accumulator entries -- 2.3x fewer tensor-core flops for the same scores;
-                               same exact fp32 rescoring behind it                               */
+                               same exact fp32 rescoring behind it.  What the Python modules use by default. */
 
 /* Problem description.  The reference instantiates c3=128, c2=64, c1=32 (n_feat=32,
  * speinet.py:53); lv2 / lv1 tensors are 2x / 4x the lv3 grids (SearchTransfer.py:36-38,44-46). */
@@ -58,13 +58,29 @@ typedef struct SpeiShape {
   int32_t c3, c2, c1;/* channels of lv3 / lv2 / lv1 (must be 128 / 64 / 32 in this version)    */
   int32_t fold_mode; /* SPEI_FOLD_* (bit mask)                                                 */
   int32_t search;    /* SPEI_SEARCH_*                                                          */
-  float eps;         /* candidate window of the bf16 pass in normalised relevance units; <=0 -> 2e-3 */
+  float eps;         /* candidate window of the bf16 pass in normalised relevance units.
+                        <= 0 (default): CERTIFIED window.  The staging pass measures the bf16 rounding residual of every query
+                        and key patch; by Cauchy-Schwarz |bf16 score - exact score| <= Delta_i for every key of query i
+                        (Delta_i = 1.01 (d_i + (1 + d_i) max_j d_j) + 1.6e-4, typically 3e-3 - 4e-3).  The tensor-core pass
+                        keeps every key within 2 Delta_i of the best bf16 score, the rescoring keeps every key whose bf16
+                        score is >= E - Delta_i (E = exact relevance of the best bf16 candidate): the true argmax cannot be
+                        outside that set.  Queries whose candidate list cannot hold the set take a second tensor-core pass.
+                        > 0: fixed window eps (round-1 behaviour with 2e-3; cheaper, exact only while no bf16 score is
+                        further than eps/2 from its exact value -- NOT certified). */
 } SpeiShape;
 
-/* Counters written by spei_search_transfer into caller memory (device, 4 x int32) when
- * `stats` is non-NULL: [0] queries re-searched exhaustively in fp32 (candidate list saturated),
- * [1] candidates rescored in fp32, [2] max |bf16 candidate score - exact score| x 1e9 over rescored
- * candidates (evidence for the eps window), [3] reserved. */
+/* Counters written by spei_search_transfer / spei_relevance_argmax / spei_rescore into caller memory (device,
+ * SPEI_STATS_WORDS x int32) when `stats` is non-NULL:
+ *  [0] queries whose candidate list saturated (handled by the second tensor-core pass)
+ *  [1] (query, key) pairs rescored exactly in fp32/fp64
+ *  [2] max |bf16 candidate score - exact score| x 1e9 over the candidates rescored in the first round
+ *  [3] != 0: the second pass ran out of capacity and the queued queries took the exhaustive fp32 search (slow, still exact)
+ *  [4] reserved
+ *  [5] (query, key) pairs emitted by the second pass
+ *  [6] certified mode: rescored candidates whose bf16 score was further than Delta_i from the exact one.  MUST be 0;
+ *      anything else means the bound does not hold on this device and the argmax is not certified.
+ *  [7] reserved */
+#define SPEI_STATS_WORDS 8
 
 int spei_version(void);
 const char *spei_last_error(void);
@@ -82,7 +98,7 @@ int spei_workspace_bytes(const SpeiShape *shape, size_t *bytes);
  *   S      [n, 1, h, w]   fp32        R_lv3_star viewed as a map           (:49)
  *   T3/T2/T1 [n, c3, h, w] / [n, c2, 2h, 2w] / [n, c1, 4h, 4w]             (:44-46)
  *   arg    [n, h*w] int64             R_lv3_star_arg, key index j = f*hr*wr + y*wr + x   (:34)  (may be NULL)
- *   stats  4 x int32 device counters (may be NULL)
+ *   stats  SPEI_STATS_WORDS x int32 device counters (may be NULL)
  */
 int spei_search_transfer(const SpeiShape *shape, const float *q, const float *k, const float *ref1,
                          const float *ref2, const float *ref3, float *S, float *T3, float *T2, float *T1,
@@ -157,9 +173,15 @@ int spei_debug_relevance_tile(const SpeiShape *shape, float *acc_out, void *work
                               void *stream);
 
 /* Copies the pipeline watchdog word of `workspace` to *host_out and synchronises `stream`.
- * 0 = no barrier of the tcgen05 kernel timed out. */
+ * 0 = no barrier of the tcgen05 kernels timed out.  (A starved barrier traps: the launch fails with a CUDA error and
+ * every later call of the process reports it; the word is readable only in -DSPEI_WATCHDOG_DRAIN debug builds.) */
 int spei_debug_error_flag(const SpeiShape *shape, void *workspace, size_t workspace_bytes, void *stream,
                           int32_t *host_out);
+
+/* host_out2[0] = clock64 span (SM cycles) of CTA 0 of the last tcgen05 search launch on `workspace`; synchronises
+ * `stream`.  Divided by the event-timed duration of that launch it gives the SM clock the kernel really ran at. */
+int spei_debug_search_cycles(const SpeiShape *shape, void *workspace, size_t workspace_bytes, void *stream,
+                             int64_t *host_out2);
 
 /* Tiling plan for `shape` on the current device, 16 x int32 (host):
  * q.orient q.tu q.tv q.Upad q.Vpad  k.orient k.tu k.tv k.Ny k.Upad k.Vpad  QT KT G maxseg num_sms */

@@ -16,6 +16,10 @@ LIB_PATH = os.environ.get("SPEINET_B200_LIB") or os.path.join(_PKG, "libspeinet_
 FOLD_CUDA, FOLD_CPU = 0, 3
 FOLD_ORDER_CPU, FOLD_TRUE_DIV = 1, 2
 SEARCH_TC, SEARCH_EXACT, SEARCH_TCS = 0, 1, 2
+STATS_WORDS = 8   # SPEI_STATS_WORDS
+STATS_NAMES = ("saturated_queries", "pairs_rescored", "max_bf16_vs_exact_x1e9", "exhaustive_fallback", "reserved4",
+               "second_pass_pairs_emitted", "certified_bound_violations", "reserved7")
+VERSION = 200
 
 
 class SpeiShape(ctypes.Structure):
@@ -45,6 +49,7 @@ SIGNATURES = {
     "spei_upsample2_bias_act": (ctypes.c_int, [ctypes.c_int32] * 4 + [_P, _P, ctypes.c_int32, _P, _P]),
     "spei_debug_relevance_tile": (ctypes.c_int, [_SH, _P, _P, ctypes.c_size_t, _P]),
     "spei_debug_error_flag": (ctypes.c_int, [_SH, _P, ctypes.c_size_t, _P, ctypes.POINTER(ctypes.c_int32)]),
+    "spei_debug_search_cycles": (ctypes.c_int, [_SH, _P, ctypes.c_size_t, _P, ctypes.POINTER(ctypes.c_int64)]),
     "spei_plan_info": (ctypes.c_int, [_SH, ctypes.POINTER(ctypes.c_int32)]),
 }
 

@@ -28,7 +28,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // Pick the orientation (and, for keys, the tile height Ny) that wastes the fewest padded positions.
 // dense:       tiles are 8 (u) x tile_v, MMA N = 8*Ny
-// tap-sharing: tiles are 14 interior (16 with halo) x tile_v, MMA N = 16*Ny; cost counts MMA columns
+// tap-sharing: tiles are 30 interior (32 with halo) x tile_v, MMA N = 32*Ny; cost counts MMA columns
 static OperandPlan plan_operand(int H, int W, bool is_key, bool shared, int force_orient = -1, double* cost_out = nullptr) {
   OperandPlan best{};
   double best_cost = 1e300;
@@ -98,6 +98,10 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.off_k32 = take(nk * Lk1 * kC3 * 4);
   p.off_qss = take(nq * L * 4);
   p.off_kss = take(nk * Lk1 * 4);
+  p.off_qrs = take(nq * L * 4);
+  p.off_krs = take(nk * Lk1 * 4);
+  p.off_dq = take(nq * L * 4);
+  p.off_dkmax = take((nq + 16) * 4);
   p.off_rq = take(nq * L * 4);
   p.off_rk = take(nk * Lk1 * 4);
   // dense: [tv*Ny][tu*8] tile-padded; tap-sharing: [tv*Ny][tu*14 + 2] with a 1-position border
@@ -107,7 +111,17 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.off_flag = take(nq * L * 4);
   p.off_packed = take(nq * L * 8);
   p.off_arg32 = take(nq * L * 4);
-  p.off_counters = take((nq + 16) * 4);  // per-item count of queries queued for the exhaustive search
+  p.off_counters = take((nq + kCntWords + 8) * 4);  // per-item count of queued queries, then the kCnt* words
+  p.off_thr = take(nq * L * 4);
+  {
+    const size_t rows = (nq * L + 127) / 128 * 128 + 128 * nq;  // every item's last tile may be partial
+    p.flag_rows = (int)(rows < (size_t)kFlagMaxRows ? rows : (size_t)kFlagMaxRows);
+  }
+  p.off_apack = take((size_t)p.flag_rows * 9 * kC3 * 2);
+  p.off_prow_thr = take((size_t)p.flag_rows * 4);
+  p.off_prow_q = take((size_t)p.flag_rows * 4);
+  p.off_emit_q = take((size_t)kFlagMaxEmit * 4);
+  p.off_emit_k = take((size_t)kFlagMaxEmit * 4);
   p.off_errflag = take(64);
   p.off_ref3n = take(nk * Lk1 * kC3 * 4);        // channels-last copies of ref_lv3 (when it is not the searched tensor)
   p.off_ref2n = take(nk * Lk1 * 4 * (kC3 / 2) * 4);  // ... and of ref_lv2 ([2hr][2wr][64])
@@ -208,9 +222,8 @@ int spei_relevance_candidates(const SpeiShape* shape, void* workspace, size_t wo
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
   if (rc) return rc;
-  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
-  return p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, (char*)workspace, (cudaStream_t)stream)
-                                   : launch_relevance_tc(p, eps, (char*)workspace, (cudaStream_t)stream);
+  return p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, shape->eps, (char*)workspace, (cudaStream_t)stream)
+                                   : launch_relevance_tc(p, shape->eps, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_rescore(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, void* workspace,
@@ -219,9 +232,7 @@ int spei_rescore(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg6
   int rc = prepare(shape, workspace, workspace_bytes, &p);
   if (rc) return rc;
   if ((rc = check_ptr(S, "S", 4)) || (rc = check_ptr(arg32, "arg32", 4))) return rc;
-  if (stats) SPEI_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));
-  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
-  return launch_rescore(p, eps, S, arg32, arg64, stats, (char*)workspace, (cudaStream_t)stream);
+  return launch_rescore(p, shape->eps, S, arg32, arg64, stats, (char*)workspace, (cudaStream_t)stream);
 }
 
 int spei_relevance_argmax(const SpeiShape* shape, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats,
@@ -232,9 +243,8 @@ int spei_relevance_argmax(const SpeiShape* shape, float* S, int32_t* arg32, int6
   if ((rc = check_ptr(S, "S", 4)) || (rc = check_ptr(arg32, "arg32", 4))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  if (stats) SPEI_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st));
-  if (shape->search == SPEI_SEARCH_EXACT) return launch_exact_all(p, S, arg32, arg64, ws, st);
-  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  if (shape->search == SPEI_SEARCH_EXACT) return launch_exact_all(p, S, arg32, arg64, stats, ws, st);
+  const float eps = shape->eps;
   rc = p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, ws, st) : launch_relevance_tc(p, eps, ws, st);
   if (rc) return rc;
   return launch_rescore(p, eps, S, arg32, arg64, stats, ws, st);
@@ -246,7 +256,7 @@ int spei_debug_relevance_tile(const SpeiShape* shape, float* acc_out, void* work
   if (rc) return rc;
   if ((rc = check_ptr(acc_out, "acc_out", 16))) return rc;
   set_debug_acc(acc_out);
-  const float eps = shape->eps > 0.f ? shape->eps : 2e-3f;
+  const float eps = shape->eps;
   return p.mode == SPEI_SEARCH_TCS ? launch_relevance_tcs(p, eps, (char*)workspace, (cudaStream_t)stream)
                                    : launch_relevance_tc(p, eps, (char*)workspace, (cudaStream_t)stream);
 }
@@ -257,6 +267,17 @@ int spei_debug_error_flag(const SpeiShape* shape, void* workspace, size_t worksp
   if (rc) return rc;
   if (!host_out) { set_error("host_out is NULL"); return SPEI_ERR_ARG; }
   SPEI_CUDA(cudaMemcpyAsync(host_out, (char*)workspace + p.off_errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SPEI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return SPEI_OK;
+}
+
+int spei_debug_search_cycles(const SpeiShape* shape, void* workspace, size_t workspace_bytes, void* stream, int64_t* host_out2) {
+  Plan p;
+  int rc = prepare(shape, workspace, workspace_bytes, &p);
+  if (rc) return rc;
+  if (!host_out2) { set_error("host_out2 is NULL"); return SPEI_ERR_ARG; }
+  host_out2[1] = 0;
+  SPEI_CUDA(cudaMemcpyAsync(host_out2, (char*)workspace + p.off_errflag + 8, sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   SPEI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return SPEI_OK;
 }
@@ -317,8 +338,9 @@ int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, c
     set_error("bad fuse_level dims n=%d h=%d w=%d scale=%d", n, h, w, scale); return SPEI_ERR_ARG;
   }
   if (c != 128 && c != 64 && c != 32) { set_error("fuse_level: c must be 128, 64 or 32 (got %d)", c); return SPEI_ERR_ARG; }
-  if ((rc = check_ptr(dec, "dec", 16)) || (rc = check_ptr(t, "t", 16)) || (rc = check_ptr(S, "S", 4)) ||
-      (rc = check_ptr(weight, "weight", 16)) || (rc = check_ptr(bias, "bias", 4)) || (rc = check_ptr(out, "out", 16)))
+  // dec / t / out: any float alignment (bases that are not 16-byte aligned take the LDG-fed kernel instead of TMA)
+  if ((rc = check_ptr(dec, "dec", 4)) || (rc = check_ptr(t, "t", 4)) || (rc = check_ptr(S, "S", 4)) ||
+      (rc = check_ptr(weight, "weight", 16)) || (rc = check_ptr(bias, "bias", 4)) || (rc = check_ptr(out, "out", 4)))
     return rc;
   if (out == dec || out == t) { set_error("fuse_level: out must not alias an input"); return SPEI_ERR_ARG; }
   return launch_fuse_level(n, c, h, w, scale, dec, t, S, weight, bias, out, (cudaStream_t)stream);

@@ -5,12 +5,11 @@
 //
 // as ONE pass over HBM (read dec, read T, write out = 3 x tensor size, the algorithmic minimum).
 //
-// Three tcgen05 kernels live in this file (DESIGN.md section 4(d) has the measurements that led from one to the next):
+// Two tcgen05 kernels live in this file (DESIGN.md section 4(d) has the measurements that led from one to the next):
 //   fuse_level_ts_kernel   DEFAULT.  Activations = A operand from tensor memory, resident weight tiles, TMA-fed residual
 //                          and TMA-store epilogue.                                    (second half of the file)
-//   fuse_level_tma_kernel  both operands in shared memory, TMA-fed; kept for A/B (SPEI_FUSE_SS=1).
 //   fuse_level_tc_kernel   LDG-fed, no alignment requirement: the path for planes whose byte stride is not a multiple of
-//                          16 (TMA needs that), described next.
+//                          16 (TMA needs that) or whose base pointers are not 16-byte aligned, described next.
 //
 // The 1x1 convolution is a skinny GEMM  D[pixel, o] = sum_k X[k, pixel] * W[o, k]  (K = 2C) that must keep
 // fp32 accuracy (1e-4 bar), so it runs as 3xTF32 on tcgen05: x = hi + lo with hi = x truncated to TF32 and
@@ -25,9 +24,8 @@
 // CTA = 160 threads: warps 0-3 produce (thread = pixel; it also owns one weight row) and later run the
 // epilogue (thread = TMEM lane = pixel: every channel store is a coalesced 128-byte row segment), warp 4
 // issues the MMAs.  Three 16-channel stages, loads prefetched one 32-channel set ahead in registers, two to
-// three CTAs per SM.  Versus the mma.sync version this replaces: 87 / 81 / 101 us -> see DESIGN.md.
+// three CTAs per SM.
 #include <cstdio>
-#include <cstdlib>
 
 #include "spei_common.cuh"
 #include "tc_ptx.cuh"
@@ -90,7 +88,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ int g_fuse_watchdog;  // set by a starved barrier wait (bounded waits: a protocol bug must not hang the GPU)
 
 template <int C>
 struct FuseTcSmem {
@@ -110,7 +107,7 @@ fuse_level_tc_kernel(const float* __restrict__ dec, const float* __restrict__ tt
                      const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out, int n_items,
                      int h, int w, int scale) {
   using L = FuseTcSmem<C>;
-  int* error_flag = &g_fuse_watchdog;
+  int* error_flag = nullptr;   // bounded waits trap on a starved barrier (tc_ptx.cuh): no sticky global state
   constexpr int K = 2 * C, NCH = K / kFKC;
   constexpr uint32_t kCols = C < 32 ? 32 : C;  // TMEM columns (power of two >= 32)
   extern __shared__ __align__(1024) uint8_t fsmem[];
@@ -287,14 +284,8 @@ fuse_level_tc_kernel(const float* __restrict__ dec, const float* __restrict__ tt
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// TMA-fed version (planes whose byte stride is a multiple of 16, i.e. plane % 4 == 0 -- every shape the model
-// produces).  Plain 4-byte loads cap the bytes a warp keeps in flight (the LDG version above reaches ~2.5 TB/s),
-// so here one elected thread streams raw [16 channel][128 pixel] fp32 boxes of dec / T through a 4-deep TMA
-// ring (32-40 KB of activations in flight per CTA; the 16-column weight slab of each stage rides in the same ring); the converter warps read a box back with thread = pixel
-// (conflict-free), split and re-store it as hi / lo UMMA tiles; the accumulator is double-buffered in TMEM and
-// drained by separate epilogue warps through a shared-memory staging tile, so that the residual read and the
-// output write are 16-byte accesses of whole 512-byte rows and overlap the next tile's conversion.
-//   warps 0-3  convert     warp 4  MMA issuer (+ TMEM alloc)     warp 5  TMA producer     warps 6-9  epilogue
+// TMA-fed pipeline constants (planes whose byte stride is a multiple of 16, i.e. plane % 4 == 0 -- every shape the
+// model produces): one elected thread streams raw [16 channel][128 pixel] fp32 boxes of dec / T through a TMA ring.
 // ---------------------------------------------------------------------------------------------------------
 #ifdef SPEI_FUSE_SPIN
 #define FUSE_WAIT mbar_wait_spin
@@ -304,284 +295,13 @@ fuse_level_tc_kernel(const float* __restrict__ dec, const float* __restrict__ tt
 constexpr uint32_t kFRawBytes = kFKC * kFM * 4;           // 8192: one raw activation box
 constexpr int kFOutCh = 16;                               // channels per epilogue staging pass
 
-
-template <int C>
-struct FuseTmaSmem {
-  using L = FuseTcSmem<C>;
-  static constexpr int kFRaw = C == 128 ? 5 : 4;                  // raw TMA ring depth (C = 128: one CTA per SM, deeper rings)
-  static constexpr int kFU = C == 128 ? 3 : 2;                    // UMMA-layout ring depth
-  static constexpr int kCtasPerSm = C == 128 ? 1 : 2;
-  // converter warps per CTA: thread = (pixel, channel part).  C = 128 runs one CTA per SM, so it gets 8 (two threads
-  // per pixel, 8 of the stage's 16 channels each): the converter chain was the longest stage of its pipeline
-  static constexpr int kConvWarps = C == 128 ? 8 : 4;
-  static constexpr int kSplit = kConvWarps / 4;
-  static constexpr int kThreads = (kConvWarps + 6) * 32;
-  static constexpr uint32_t kRaw = 0;
-  static constexpr uint32_t kWBox = C * kFKC * 4;                 // raw weight box [C rows][16 k] fp32
-  static constexpr uint32_t kRawStage = kFRawBytes + kWBox;       // X box + W box per TMA stage
-  static constexpr uint32_t kUmma = kFRaw * kRawStage;
-  static constexpr uint32_t kOut = kUmma + kFU * L::kStage;
-  static constexpr uint32_t kBars = kOut + 2 * kFOutCh * kFM * 4;   // (staging tile double-buffered) raw_full[4] raw_empty[4] u_full[2] u_empty[2] acc_full[2] acc_empty[2]
-  static constexpr uint32_t kNumBars = 2 * kFRaw + 2 * kFU + 4;
-  static constexpr uint32_t kTotal = kBars + 8 * kNumBars + 16;
-};
-
-template <int C>
-__global__ void __launch_bounds__(FuseTmaSmem<C>::kThreads, FuseTmaSmem<C>::kCtasPerSm)
-fuse_level_tma_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_constant__ CUtensorMap tm_t,
-                      const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ dec, const float* __restrict__ S, const float* __restrict__ weight,
-                      const float* __restrict__ bias, float* __restrict__ out, int n_items, int h, int w, int scale) {
-  using L = FuseTcSmem<C>;
-  using SM = FuseTmaSmem<C>;
-  constexpr int kFRaw = SM::kFRaw, kFU = SM::kFU;
-  constexpr int CW = SM::kConvWarps, kSplit = SM::kSplit, kConvThreads = CW * 32;
-  constexpr int kChunks = kFKC / 4 / kSplit;      // 4-channel chunks of a stage per converter thread
-  int* error_flag = &g_fuse_watchdog;
-  constexpr int K = 2 * C, NCH = K / kFKC;
-  constexpr uint32_t kCols = 2 * C < 32 ? 32 : 2 * C;   // two accumulators
-  extern __shared__ __align__(1024) uint8_t fsmem[];
-  const uint32_t s0 = smem_u32(fsmem);
-  const uint32_t bar_rfull = s0 + SM::kBars, bar_rempty = bar_rfull + 8 * kFRaw, bar_ufull = bar_rempty + 8 * kFRaw,
-                 bar_uempty = bar_ufull + 8 * kFU, bar_afull = bar_uempty + 8 * kFU, bar_aempty = bar_afull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fsmem + SM::kBars + 8 * SM::kNumBars);
-  float* ostage = reinterpret_cast<float*>(fsmem + SM::kOut);   // [2][16 ch][128 px]
-  const float* raw = reinterpret_cast<const float*>(fsmem + SM::kRaw);
-
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int hs = h * scale, wsz = w * scale;
-  const size_t plane = (size_t)hs * wsz;
-  const long long tpi = (long long)((plane + kFM - 1) / kFM), total = tpi * n_items;
-
-  if (t == 0) {
-    for (int s = 0; s < kFRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, kConvThreads); }
-    for (int s = 0; s < kFU; ++s) { mbar_init(bar_ufull + 8 * s, kConvThreads); mbar_init(bar_uempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, kFM); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dec) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_t) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
-  }
-  if (warp == CW) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < CW) {
-    // ====== convert (thread = pixel x channel part; threads with px < C also convert their part of weight row px) ======
-    const int px = t & (kFM - 1), part = t / kFM;   // part < kSplit: chunks [part * kChunks, (part + 1) * kChunks) of the stage
-    const bool wrow = px < C;
-    long long tile = blockIdx.x;
-    int g = 0;
-    [[maybe_unused]] long long pf_t0 = clock64(), pf_rfull = 0, pf_uempty = 0;
-#pragma unroll 1
-    for (; tile < total; tile += gridDim.x) {
-#pragma unroll 1
-      for (int kc = 0; kc < NCH; ++kc, ++g) {
-        const int r = g % kFRaw, s = g % kFU;
-        FPROF_T(pf_rfull, FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kFRaw) & 1), error_flag));
-        const float* rbox = raw + (size_t)r * (SM::kRawStage / 4);
-        float x[4 * kChunks];
-#pragma unroll
-        for (int c = 0; c < 4 * kChunks; ++c) x[c] = rbox[(part * 4 * kChunks + c) * kFM + px];
-        // weight row px of this stage: 16-byte chunks at a 64-byte thread stride.  Read in a fixed chunk order the 8
-        // threads of a 128-bit shared-memory phase hit only two 4-bank groups (4-way conflict; ncu: 45 % of the kernel's
-        // LSU wavefronts were conflicts), so thread px starts at chunk (px >> 1) % kChunks of its part and wraps.  The
-        // chunk index only enters address arithmetic (load here, store below), never a register index.
-        const int jrot = (px >> 1) & (kChunks - 1);
-        float4 wv[kChunks];
-#pragma unroll
-        for (int j = 0; j < kChunks; ++j)
-          wv[j] = wrow ? reinterpret_cast<const float4*>(rbox + kFRawBytes / 4 + px * kFKC)[part * kChunks + ((j + jrot) & (kChunks - 1))]
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        // generic-proxy reads must be ordered before the async-proxy (TMA) refill of this box: without this
-        // fence the refill raced with the reads (measured: sporadic wrong tiles at C = 128, where the ring wraps)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar_rempty + 8 * r);
-        if (g >= kFU) FPROF_T(pf_uempty, FUSE_WAIT(bar_uempty + 8 * s, (uint32_t)((g / kFU - 1) & 1), error_flag));
-        const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
-#ifndef SPEI_FUSE_NO_CONV
-#pragma unroll
-        for (int j = 0; j < kChunks; ++j) {
-          const float x4[4] = {x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]};
-          uint4 hi, lo;
-          ft_split4(x4, hi, lo);
-          const uint32_t ja = (uint32_t)(part * kChunks + j);
-          st_shared_v4(a_hi + ja * L::kALBO + px * 16, hi);
-          st_shared_v4(a_lo + ja * L::kALBO + px * 16, lo);
-          if (wrow) {
-            const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
-            ft_split4(w4, hi, lo);
-            const uint32_t jj = (uint32_t)(part * kChunks + ((j + jrot) & (kChunks - 1)));
-            st_shared_v4(b_hi + jj * L::kBLBO + px * 16, hi);
-            st_shared_v4(b_lo + jj * L::kBLBO + px * 16, lo);
-          }
-        }
-#else
-        if (x[0] == 123.456f && wv[0].x == 3.f) st_shared_v4(a_hi, make_uint4(1, 2, 3, 4));  // keep the loads alive
-#endif
-#ifndef SPEI_FUSE_NO_FENCE2
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> visible to the MMA (async proxy)
-#endif
-        mbar_arrive(bar_ufull + 8 * s);
-      }
-    }
-#ifdef SPEI_FUSE_PROF
-    if (blockIdx.x == 3 && (t == 0 || t == 100)) printf("C=%d conv t%d: total %lld wait_rfull %lld wait_uempty %lld stages %d\n", C, t, clock64() - pf_t0, pf_rfull, pf_uempty, g);
-#endif
-  } else if (warp == CW) {
-    // ======================================== MMA issuer ========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
-      int g = 0, it = 0;
-      [[maybe_unused]] long long pf_t0 = clock64(), pf_aempty = 0, pf_ufull = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const uint32_t ab = it & 1;
-        if (it >= 2) FPROF_T(pf_aempty, FUSE_WAIT(bar_aempty + 8 * ab, (uint32_t)((it / 2 - 1) & 1), error_flag));
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * C;
-        for (int kc = 0; kc < NCH; ++kc, ++g) {
-          const int s = g % kFU;
-          FPROF_T(pf_ufull, FUSE_WAIT(bar_ufull + 8 * s, (uint32_t)((g / kFU) & 1), error_flag));
-          tc_fence_after();
-          const uint32_t a_hi = s0 + SM::kUmma + s * L::kStage, a_lo = a_hi + L::kABytes, b_hi = a_lo + L::kABytes, b_lo = b_hi + L::kBBytes;
-#pragma unroll
-          for (uint32_t kk = 0; kk < kFKC / 8; ++kk) {
-            const uint64_t dah = umma_desc_kmajor(a_hi + kk * 2 * L::kALBO, L::kALBO, 128);
-            const uint64_t dal = umma_desc_kmajor(a_lo + kk * 2 * L::kALBO, L::kALBO, 128);
-            const uint64_t dbh = umma_desc_kmajor(b_hi + kk * 2 * L::kBLBO, L::kBLBO, 128);
-            const uint64_t dbl = umma_desc_kmajor(b_lo + kk * 2 * L::kBLBO, L::kBLBO, 128);
-#ifndef SPEI_FUSE_NO_MMA   // (experiment switch: hand-off latency without the MMAs)
-            tc_mma_tf32(d_tmem, dal, dbh, idesc, (kc | kk) != 0);  // small terms first
-            tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-            tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
-#endif
-          }
-          tc_commit(bar_uempty + 8 * s);
-        }
-        tc_commit(bar_afull + 8 * ab);
-      }
-#ifdef SPEI_FUSE_PROF
-      if (blockIdx.x == 3) printf("C=%d mma: total %lld wait_aempty %lld wait_ufull %lld tiles %d\n", C, clock64() - pf_t0, pf_aempty, pf_ufull, it);
-#endif
-    }
-  } else if (warp == CW + 1) {
-    // ======================================== TMA producer ========================================
-    if (lane == 0) {
-      int g = 0;
-      [[maybe_unused]] long long pf_t0 = clock64(), pf_rempty = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int n = (int)(tile / tpi);
-        const int p0 = (int)((tile - (long long)n * tpi) * kFM);
-        for (int kc = 0; kc < NCH; ++kc, ++g) {
-          const int r = g % kFRaw;
-          if (g >= kFRaw) FPROF_T(pf_rempty, FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kFRaw - 1) & 1), error_flag));
-          mbar_arrive_expect_tx(bar_rfull + 8 * r, SM::kRawStage);
-          const int ch0 = kc * kFKC;
-          tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage, ch0 < C ? &tm_dec : &tm_t, bar_rfull + 8 * r, p0, n * C + (ch0 < C ? ch0 : ch0 - C));
-          tma_load_2d(s0 + SM::kRaw + r * SM::kRawStage + kFRawBytes, &tm_w, bar_rfull + 8 * r, ch0, 0);  // weight columns ch0..ch0+15
-        }
-      }
-#ifdef SPEI_FUSE_PROF
-      if (blockIdx.x == 3) printf("C=%d tma: total %lld wait_rempty %lld\n", C, clock64() - pf_t0, pf_rempty);
-#endif
-    }
-  } else {
-    // ================================ epilogue (thread = TMEM lane = pixel) ================================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int px = q * 32 + lane;
-    const int te = (warp - (CW + 2)) * 32 + lane;  // 0..127: cooperative row mapping of the store phase
-    auto soft_weight = [&](long long tile) {  // bicubic upsampled S at this thread's pixel of `tile`
-      const int n = (int)(tile / tpi);
-      const size_t p = (size_t)(tile - (long long)n * tpi) * kFM + px;
-      if (p >= plane) return 0.f;
-      const int oy = (int)(p / wsz), ox = (int)(p % wsz);
-      const float* S_n = S + (size_t)n * h * w;
-      return scale == 1 ? __ldg(S_n + (size_t)oy * w + ox) : ft_bicubic(S_n, h, w, oy, ox, 1.0f / (float)scale);
-    };
-    // residual rows (16-byte loads of whole 512-byte channel rows) are prefetched one staging pass ahead, across
-    // tile boundaries: the epilogue never waits for a load it has just issued
-    const int px4 = (te & 31) * 4;
-    auto load_residual = [&](long long tile_, int c0, float4 (&dv)[kFOutCh / 4]) {
-      const int n = (int)(tile_ / tpi);
-      const size_t p0 = (size_t)(tile_ - (long long)n * tpi) * kFM;
-      const bool rin = tile_ < total && p0 + px4 < plane;
-#pragma unroll
-      for (int k = 0; k < kFOutCh / 4; ++k) {
-        const int ch = (te >> 5) + 4 * k;
-        dv[k] = rin ? __ldg(reinterpret_cast<const float4*>(dec + ((size_t)n * C + c0 + ch) * plane + p0 + px4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    long long tile = blockIdx.x;
-    float sw = tile < total ? soft_weight(tile) : 0.f;
-    float4 dnext[kFOutCh / 4];
-    load_residual(tile, 0, dnext);
-    int it = 0, pass = 0;
-    [[maybe_unused]] long long pf_t0 = clock64(), pf_afull = 0;
-#pragma unroll 1
-    for (; tile < total; tile += gridDim.x, ++it) {
-      const uint32_t ab = it & 1;
-      const float sw_next = tile + gridDim.x < total ? soft_weight(tile + gridDim.x) : 0.f;  // taps in flight during this tile
-      const int n = (int)(tile / tpi);
-      const size_t p0 = (size_t)(tile - (long long)n * tpi) * kFM;
-      const bool rin = p0 + px4 < plane;
-      FPROF_T(pf_afull, FUSE_WAIT(bar_afull + 8 * ab, (uint32_t)((it / 2) & 1), error_flag));
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ab * C + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += kFOutCh, ++pass) {
-        float4 dv[kFOutCh / 4];
-#pragma unroll
-        for (int k = 0; k < kFOutCh / 4; ++k) dv[k] = dnext[k];
-        if (c0 + kFOutCh < C) load_residual(tile, c0 + kFOutCh, dnext); else load_residual(tile + gridDim.x, 0, dnext);
-        float* ost = ostage + (pass & 1) * (kFOutCh * kFM);   // double-buffered staging tile: one barrier per pass
-        uint32_t a[16];
-        tc_ld16(taddr + c0, a);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) ost[i * kFM + px] = (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#ifdef SPEI_FUSE_NO_EPI
-        if (rin && dv[0].x == 123.456f)
-#else
-        if (rin)
-#endif
-        {
-#pragma unroll
-          for (int k = 0; k < kFOutCh / 4; ++k) {
-            const int ch = (te >> 5) + 4 * k;
-            const float4 v = *reinterpret_cast<const float4*>(ost + ch * kFM + px4);
-            *reinterpret_cast<float4*>(out + ((size_t)n * C + c0 + ch) * plane + p0 + px4) =
-                make_float4(dv[k].x + v.x, dv[k].y + v.y, dv[k].z + v.z, dv[k].w + v.w);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_aempty + 8 * ab);   // this accumulator may be overwritten by the tile after next
-      sw = sw_next;
-    }
-#ifdef SPEI_FUSE_PROF
-    if (blockIdx.x == 3 && te == 0) printf("C=%d epi: total %lld wait_afull %lld tiles %d\n", C, clock64() - pf_t0, pf_afull, it);
-#endif
-  }
-
-  __syncthreads();
-  if (warp == CW) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // v3 ("TS"): the activations are the A operand FROM TENSOR MEMORY.
 //
-// clock64 accounting of the kernel above (SPEI_FUSE_PROF, round 1): the converter threads are busy 87 % of the time, the
-// MMA issuer waits for operands 60 %, the TMA producer waits for a free slot 86 %; every activation float crosses
-// shared memory as 4 B TMA write + 4 B LDS + 8 B hi/lo STS + 12 B UMMA operand reads (28 B per 4 B of HBM traffic), and
-// the weights again per 128-pixel tile: the shared-memory pipe, not HBM, bounds that design.  Here
+// Its predecessor (round 1, removed) kept both operands in shared memory; clock64 accounting showed the converter threads
+// busy 87 % of the time, the MMA issuer waiting for operands 60 %, the TMA producer waiting for a free slot 86 %: every
+// activation float crossed shared memory as 4 B TMA write + 4 B LDS + 8 B hi/lo STS + 12 B UMMA operand reads (28 B per
+// 4 B of HBM traffic), and the weights again per 128-pixel tile: the shared-memory pipe, not HBM, bounded that design.  Here
 //   * the converter thread (= pixel = TMEM lane) reads its 16 channels of the raw TMA box, splits them and writes hi / lo
 //     straight into a ring of A tiles in tensor memory (tcgen05.st, 32 columns per stage); the MMA reads A from there
 //     (tcgen05.mma [d], [a], b-desc): per activation float shared memory now carries 4 B TMA write + 4 B LDS;
@@ -641,7 +361,7 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
   constexpr int kRaw = F::kRaw, kU = F::kU, kE = F::kE, CW = F::kConvWarps, kConvThreads = CW * 32, NCH = F::NCH;
   constexpr int kCh = kFKC / F::kSplit;          // channels of a stage per converter thread (16 or 8)
   constexpr int K = 2 * C;
-  int* error_flag = &g_fuse_watchdog;
+  int* error_flag = nullptr;   // bounded waits trap on a starved barrier (tc_ptx.cuh): no sticky global state
   extern __shared__ __align__(1024) uint8_t fsmem[];
   const uint32_t s0 = smem_u32(fsmem);
   const uint32_t bar_rfull = s0 + F::kOffBars, bar_rempty = bar_rfull + 8 * kRaw, bar_afull = bar_rempty + 8 * kRaw,
@@ -935,29 +655,16 @@ static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, c
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level weight) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
   }
-  static const bool ss = getenv("SPEI_FUSE_SS") != nullptr;   // A/B switch: the shared-memory-operand kernel (v2)
-  if (!ss) {
-    const int smem = (int)FuseTsCfg<C>::kTotal;
-    SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    int dev = 0, sms = 0;
-    SPEI_CUDA(cudaGetDevice(&dev));
-    SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTsCfg<C>::kCtasPerSm;
-    CUtensorMap tmo;
-    if ((rc = make_plane_map(enc, &tmo, out, (size_t)n * C, plane))) return rc;
-    fuse_level_ts_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTsCfg<C>::kThreads, smem, st>>>(tmd, tmt, tmw, tmo, S, weight, bias, n, h, w, scale);
-    SPEI_CUDA(cudaGetLastError());
-    return SPEI_OK;
-  }
-  const int smem = (int)FuseTmaSmem<C>::kTotal;
-  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_tma_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  const int smem = (int)FuseTsCfg<C>::kTotal;
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   int dev = 0, sms = 0;
   SPEI_CUDA(cudaGetDevice(&dev));
   SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTmaSmem<C>::kCtasPerSm;
-  fuse_level_tma_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTmaSmem<C>::kThreads, smem, st>>>(tmd, tmt, tmw, dec, S, weight, bias, out, n, h, w, scale);
+  const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTsCfg<C>::kCtasPerSm;
+  CUtensorMap tmo;
+  if ((rc = make_plane_map(enc, &tmo, out, (size_t)n * C, plane))) return rc;
+  fuse_level_ts_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTsCfg<C>::kThreads, smem, st>>>(tmd, tmt, tmw, tmo, S, weight, bias, n, h, w, scale);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }
@@ -978,12 +685,13 @@ static int launch_fuse_tc_t(int n, int h, int w, int scale, const float* dec, co
   return SPEI_OK;
 }
 
-int launch_fuse_level_tc(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
-                         const float* weight, const float* bias, float* out, cudaStream_t st) {
+int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
+                      const float* weight, const float* bias, float* out, cudaStream_t st) {
   if (n > 65535) { set_error("fuse_level: n too large"); return SPEI_ERR_ARG; }
   const size_t plane = (size_t)h * scale * w * scale;
-  static const bool no_tma = getenv("SPEI_FUSE_NO_TMA") != nullptr;  // A/B switch
-  if (!no_tma && plane % 4 == 0 && (long long)n * c < (1ll << 31) && plane < (1ull << 31)) {  // TMA needs 16-byte plane strides
+  // TMA needs 16-byte plane strides and 16-byte aligned bases; anything else takes the LDG-fed kernel
+  const bool aligned = (((uintptr_t)dec | (uintptr_t)t | (uintptr_t)out | (uintptr_t)weight) & 15) == 0;
+  if (aligned && plane % 4 == 0 && (long long)n * c < (1ll << 31) && plane < (1ull << 31)) {
     if (c == 128) return launch_fuse_tma_t<128>(n, h, w, scale, dec, t, S, weight, bias, out, st);
     if (c == 64) return launch_fuse_tma_t<64>(n, h, w, scale, dec, t, S, weight, bias, out, st);
     if (c == 32) return launch_fuse_tma_t<32>(n, h, w, scale, dec, t, S, weight, bias, out, st);

@@ -56,6 +56,8 @@ struct TcParams {
   uint32_t idesc, stage_bytes, k_lbo;
   float win;         // candidate window (normalised relevance units, slightly wider than the rescoring's eps)
   const float* rq;   // query reciprocal patch norms [n*L]: the epilogue's scores lack this factor
+  const float* dq;     // per-query relative bf16 residual norm (stage_norm.cu)
+  const int* dkmax;    // per-item maximum over the keys, float bits
   const float* rkpad;
   float* cval;
   int32_t* cidx;
@@ -82,6 +84,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
   const long long pb = (long long)b * p.P / p.G, pe = (long long)(b + 1) * p.P / p.G;
+  const long long cyc0 = clock64();   // CTA 0 publishes its clock64 span: the SM clock this kernel really ran at (bench.py)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -200,7 +203,12 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
         const int u = qtu * kTileU + (m & 7), v = qtv * kQTileV + (m >> 3);
         qlin = (u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
-        winq = qlin >= 0 ? p.win / __ldg(p.rq + qlin) : 0.f;
+        winq = 0.f;
+        if (qlin >= 0) {
+          // fixed window (eps > 0) or the certified one: every key within 2 * Delta of the best bf16 score stays a candidate
+          const float wn = p.win > 0.f ? p.win : 2.04f * certified_delta(__ldg(p.dq + qlin), __int_as_float(__ldg(p.dkmax + ix.item)));
+          winq = wn / __ldg(p.rq + qlin);
+        }
 #ifdef SPEI_NO_WINDOW  // A/B only: plain top-k insertion
         winq = INFINITY;
 #endif
@@ -300,6 +308,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (b == 0 && threadIdx.x == 0) *reinterpret_cast<long long*>(p.error_flag + 2) = clock64() - cyc0;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -355,8 +364,10 @@ int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st) {
   t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
   t.k_lbo = (uint32_t)(p.k.tile_v + 2) * kRowBytes;
   t.stage_bytes = kCGS * t.k_lbo;
-  t.win = eps * 1.02f;  // a hair wider than the rescoring window: the two sides round differently
+  t.win = eps > 0.f ? eps * 1.02f : 0.f;  // a hair wider than the rescoring window: the two sides round differently
   t.rq = (const float*)(ws + p.off_rq);
+  t.dq = (const float*)(ws + p.off_dq);
+  t.dkmax = (const int*)(ws + p.off_dkmax);
   t.rkpad = (const float*)(ws + p.off_rkpad);
   t.cval = (float*)(ws + p.off_cval);
   t.cidx = (int32_t*)(ws + p.off_cidx);

@@ -1,17 +1,23 @@
 // Kernel (b'): exactness layer behind the bf16 tcgen05 relevance pass
 // (/root/reference/model/SearchTransfer.py:33-34: R = bmm(K^, Q^); R_star, arg = max(R, dim=1)).
 //
-//  rescore_kernel       one warp per query: merges the per-segment top-k candidate lists of the bf16
-//                       pass, keeps those within eps of the best bf16 score, recomputes their relevance
-//                       exactly (fp32 operands, 4-term fp32 partial dots accumulated in fp64) and picks the maximum with
-//                       torch.max's first-index tie-break.  A query whose candidate list is saturated
-//                       (its k-th candidate is still inside the eps window, so a better key might have
-//                       been dropped) is queued for the exhaustive search below.
-//  exact_search_kernel  exhaustive fp32 search on CUDA cores for a list of queries (or all of them:
-//                       SPEI_SEARCH_EXACT, the on-GPU checker).  64 queries x 64 keys register-tiled
-//                       implicit GEMM over the 9 taps x 128 channels, packed (score, ~index) atomicMax.
-//  unpack_kernel        writes S / arg for exhaustively searched queries.
+//  rescore_kernel       one warp per query.  Merges the per-segment top-k candidate lists of the bf16 pass, recomputes the
+//                       relevance of the best bf16 candidate exactly (fp32 operands, fp64 accumulation) -> E, and from E
+//                       the threshold T below which no key can be the argmax:
+//                         certified mode (eps <= 0, default):  T = E - Delta_i, Delta_i = the bound on |bf16 score - exact
+//                           score| over ALL keys derived from the measured rounding residuals (stage_norm.cu,
+//                           certified_delta()).  The true argmax j* has exact score >= E, hence bf16 score >= E - Delta_i.
+//                         fixed window (eps > 0, uncertified): T = best bf16 score - eps.
+//                       Every other candidate with bf16 score >= T is rescored exactly and the maximum is taken with
+//                       torch.max's first-index tie-break.  A query one of whose lists is SATURATED (its k-th entry is
+//                       still >= T, so keys >= T may have been dropped) is queued, with its threshold, for the second
+//                       tcgen05 pass (relevance_flagged.cu), which enumerates every key >= T of that query.
+//  exact_search_kernel  exhaustive fp32 search on CUDA cores: SPEI_SEARCH_EXACT (the on-GPU checker) and the last resort
+//                       when the second pass runs out of capacity.  64 queries x 64 keys register-tiled implicit GEMM over
+//                       the 9 taps x 128 channels, packed (score, ~index) atomicMax.
+//  unpack_kernel        writes S / arg of the queued queries from the packed maxima.
 #include "spei_common.cuh"
+#include "exact_score.cuh"
 
 namespace spei {
 
@@ -19,40 +25,31 @@ __host__ __device__ inline long long cta_of_pair_d(long long p, long long P, int
   return ((p + 1) * (long long)G - 1) / P;
 }
 
-__device__ __forceinline__ unsigned flip_f32(float f) {
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unflip_f32(unsigned u) {
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-__device__ __forceinline__ unsigned long long pack_score(float s, int j) {
-  return ((unsigned long long)flip_f32(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
-}
-
 struct RescoreParams {
   int n, rf, H, W, Hr, Wr;
   int q_orient, q_tu, q_tile_u, q_tile_v, nlist;  // query tile grid (to find a query's tile -> its segment count)
   int QT, KT, G, maxseg;
   long long P;
-  float eps;
-  const float *q32, *k32, *rq, *rk, *qss;
+  float eps;                  // > 0: fixed window; <= 0: certified
+  const float *q32, *k32, *rq, *rk, *qss, *dq;
+  const int* dkmax;
   const float* cval;
   const int32_t* cidx;
   float* S;
   int32_t* arg32;
   int64_t* arg64;
-  int32_t* flag_list;   // [n][L]
-  int32_t* flag_count;  // [n]
+  int32_t* flag_list;         // [n][L] queries queued for the second pass
+  int32_t* counters;          // [n] queued per item, then the kCnt* words
+  float* thr;                 // [n*L] threshold of a queued query in accumulator units (T / rq)
+  unsigned long long* packed; // [n*L] running (score, ~key) maxima of the queued queries
   int32_t* stats;
 };
 
 __global__ void __launch_bounds__(256, 4)
 rescore_kernel(const RescoreParams p) {
-  // The kernel is latency bound (every phase is a dependent L2 round trip), so it is written for
-  // occupancy and early issue: the query's 9x128 patch goes to shared memory with cp.async (no register
-  // staging, <= 64 registers -> 32 warps per SM) and every load that does not depend on another is
-  // issued before the first branch.
+  // L2-bandwidth bound (each exact score reads the 4.6 KB key patch): written for occupancy and early issue -- the
+  // query's 9x128 patch goes to shared memory with cp.async (no register staging, <= 64 registers -> 32 warps per SM)
+  // and every load that does not depend on another is issued before the first branch.
   __shared__ __align__(16) float qpatch[8][9 * kC3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long wq = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -61,21 +58,7 @@ rescore_kernel(const RescoreParams p) {
   const int n = (int)(wq / L), ql = (int)(wq % L);
   const int y = ql / p.W, x = ql % p.W;
   const int lk1 = p.Hr * p.Wr;
-
-  // query patch -> shared memory (zero-filled taps outside the image)
-  {
-    const float* qimg = p.q32 + (size_t)n * L * kC3;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      const bool in = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-      const float* src = qimg + ((size_t)(in ? yy : y) * p.W + (in ? xx : x)) * kC3 + lane * 4;
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(&qpatch[warp][t * kC3 + lane * 4]);
-      const int sz = in ? 16 : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  load_query_patch_async(&qpatch[warp][0], p.q32 + (size_t)n * L * kC3, y, x, p.H, p.W, lane);
 
   // which query tile is this, and into how many key segments was it split?
   const int u = p.q_orient == 0 ? x : y, v = p.q_orient == 0 ? y : x;
@@ -87,7 +70,7 @@ rescore_kernel(const RescoreParams p) {
   const float* cv = p.cval + (size_t)wq * p.maxseg * p.nlist * kTopK;
   const int32_t* ci = p.cidx + (size_t)wq * p.maxseg * p.nlist * kTopK;
 
-  // independent loads first: patch energy (zero test), query norm, first 32 candidates
+  // independent loads first: patch energy (zero test), query norm, residual bound, first 32 candidates
   float s = 0.f;
   {
     const float* ss = p.qss + (size_t)n * L;
@@ -98,6 +81,7 @@ rescore_kernel(const RescoreParams p) {
     }
   }
   const float rq = __ldg(p.rq + wq);
+  const float delta = p.eps > 0.f ? 0.f : certified_delta(__ldg(p.dq + wq), __int_as_float(__ldg(p.dkmax + n)));
   int j0 = -1;
   float v0 = 0.f;
   if (lane < ncand) { j0 = __ldg(ci + lane); v0 = __ldg(cv + lane); }
@@ -112,38 +96,53 @@ rescore_kernel(const RescoreParams p) {
     return;
   }
 
-  // pass 1: best bf16 score
+  // pass 1: best bf16 score and its key
   float bn = j0 >= 0 ? v0 * rq : -INFINITY;
+  int bj = j0;
   for (int e = lane + 32; e < ncand; e += 32) {
     const int j = __ldg(ci + e);
-    if (j >= 0) bn = fmaxf(bn, __ldg(cv + e) * rq);
+    const float vb = __ldg(cv + e) * rq;
+    if (j >= 0 && vb > bn) { bn = vb; bj = j; }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) bn = fmaxf(bn, __shfl_xor_sync(0xffffffffu, bn, o));
-  const float thr = bn - p.eps;
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, bn, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ob > bn || (ob == bn && (unsigned)oj < (unsigned)bj)) { bn = ob; bj = oj; }   // (unsigned): -1 loses
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]) + lane;  // tap t at qv[t * 32]
+  auto exact = [&](int jj) {
+    const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
+    const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
+    return exact_relevance(qv, p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
+  };
+  // every query has at least one candidate: its lists hold the best keys of every segment (bj >= 0)
+  const float E = exact(bj);
+  const float thr = p.eps > 0.f ? bn - p.eps : E - delta;
+  float max_err = fabsf(bn - E);
+  int nres = 1, nviol = (p.eps <= 0.f && max_err > delta) ? 1 : 0;
 
-  // saturation: the last (smallest) entry of some segment is still inside the window
+  // saturation: the last (smallest) entry of some list is still at or above the threshold
   bool sat = false;
   for (int sg = lane; sg < nlists; sg += 32) {
     const int e = sg * kTopK + (kTopK - 1);
     if (__ldg(ci + e) >= 0 && __ldg(cv + e) * rq >= thr) sat = true;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
   if (__any_sync(0xffffffffu, sat)) {
     if (lane == 0) {
-      const int pos = atomicAdd(p.flag_count + n, 1);
+      const int pos = atomicAdd(p.counters + n, 1);
       p.flag_list[(size_t)n * L + pos] = ql;
-      if (p.stats) atomicAdd(p.stats + 0, 1);
+      p.thr[wq] = thr / rq;
+      p.packed[wq] = pack_score(E, bj);
+      if (p.stats) { atomicAdd(p.stats + 0, 1); atomicAdd(p.stats + 1, 1); atomicMax(p.stats + 2, (int)(max_err * 1e9f)); }
     }
-    return;  // S / arg are written by unpack_kernel after the exhaustive search
+    return;  // S / arg are written by unpack_kernel after the second pass
   }
-  const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]) + lane;  // tap t at qv[t * 32]
 
-  // pass 2: exact relevance of every kept candidate
-  unsigned long long best = 0ull;
-  int nres = 0;
-  float max_err = 0.f;  // largest |bf16 score - exact score| seen: evidence for the eps window
+  // pass 2: exact relevance of every other candidate at or above the threshold
+  unsigned long long best = pack_score(E, bj);
   for (int e0 = 0; e0 < ncand; e0 += 32) {
     const int e = e0 + lane;
     int j = -1;
@@ -151,7 +150,7 @@ rescore_kernel(const RescoreParams p) {
     if (e < ncand) {
       j = e0 == 0 ? j0 : __ldg(ci + e);
       vb = (e0 == 0 ? v0 : __ldg(cv + e)) * rq;
-      if (j >= 0 && !(vb >= thr)) j = -1;
+      if (j == bj || !(vb >= thr)) j = -1;
     }
     unsigned m = __ballot_sync(0xffffffffu, j >= 0);
     while (m) {
@@ -159,47 +158,23 @@ rescore_kernel(const RescoreParams p) {
       m &= m - 1;
       const int jj = __shfl_sync(0xffffffffu, j, src);
       const float vbb = __shfl_sync(0xffffffffu, vb, src);
-      const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
-      const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      // Each lane owns 4 channels of every tap: their 4 products are summed in fp32 (one rounding of ~6e-8 relative per
-      // product, ~2e-9 absolute on a normalised score -- four orders of magnitude inside the 1e-5 near-tie rule) and the 9
-      // tap partials, then the 32 lanes, are accumulated in fp64.  The all-fp64 version (8 F2F + 4 DFMA per lane and tap)
-      // kept the conversion pipe 40 % busy (ncu, round 1) and was the kernel's top pipe.
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // three independent chains (taps t % 3), fixed order
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
-        if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
-          const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
-          const float4 qq = qv[t * 32];
-          float part = qq.x * kv.x;
-          part = fmaf(qq.y, kv.y, part);
-          part = fmaf(qq.z, kv.z, part);
-          part = fmaf(qq.w, kv.w, part);
-          if (t % 3 == 0) acc0 += (double)part;
-          else if (t % 3 == 1) acc1 += (double)part;
-          else acc2 += (double)part;
-        }
-      }
-      double acc = (acc0 + acc1) + acc2;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
-      const float score = (float)(acc * (double)rq * (double)rk);
+      const float score = exact(jj);
       const unsigned long long key = pack_score(score, jj);
       best = key > best ? key : best;
-      max_err = fmaxf(max_err, fabsf(vbb - score));
+      const float err = fabsf(vbb - score);
+      max_err = fmaxf(max_err, err);
+      if (p.eps <= 0.f && err > delta) ++nviol;
       ++nres;
     }
   }
   if (lane == 0) {
-    const float s = unflip_f32((unsigned)(best >> 32));
-    const int j = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
-    p.S[wq] = s; p.arg32[wq] = j;
+    const int j = packed_key(best);
+    p.S[wq] = packed_score(best); p.arg32[wq] = j;
     if (p.arg64) p.arg64[wq] = j;
     if (p.stats) {
       atomicAdd(p.stats + 1, nres);
       atomicMax(p.stats + 2, (int)(max_err * 1e9f));
+      if (nviol) atomicAdd(p.stats + 6, nviol);
     }
   }
 }
@@ -210,10 +185,10 @@ rescore_kernel(const RescoreParams p) {
 struct ExactParams {
   int n, rf, H, W, Hr, Wr;
   int key_splits;
-  int small_max;              // list mode: items with <= small_max queued queries belong to exact_small_kernel
   const float *q32, *k32, *rq, *rk;
   const int32_t* list;        // [n][L] query ids, or NULL = all queries
   const int32_t* list_count;  // [n], or NULL
+  const int32_t* enable;      // list mode: run only if *enable != 0 (the second pass ran out of capacity); NULL = always
   unsigned long long* packed; // [n][L]
 };
 
@@ -226,8 +201,8 @@ exact_search_kernel(const ExactParams p) {
   __shared__ __align__(16) float Bs[kEC][kEK];
   const int n = blockIdx.z;
   const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
+  if (p.enable && *reinterpret_cast<const volatile int32_t*>(p.enable) == 0) return;
   const int nq = p.list ? __ldg(p.list_count + n) : L;
-  if (p.list && nq <= p.small_max) return;  // handled by exact_small_kernel
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int lq = t & 63, lpart = t >> 6;  // loader role: one of 64 rows, 8 of the 32 channels
   // grid-stride over blocks of 64 queries: the queued-query count is only known on the device
@@ -325,71 +300,13 @@ exact_search_kernel(const ExactParams p) {
   }  // query blocks
 }
 
-// Few queued queries (the common case: a handful per frame): the 64-query tile of the kernel above
-// would be almost empty, so a warp brute-forces (query, key) pairs instead -- the query's 9x128 patch
-// lives in registers, each key costs nine coalesced 512-byte reads and an fp64 dot, exactly the
-// arithmetic of rescore_kernel.  grid: (key blocks, 1, n); items with more than kSmallMax queued
-// queries are left to exact_search_kernel (which skips the others).
-constexpr int kSmallMax = 64;
-
-// grid: (key blocks, query lanes, n)
-__global__ void __launch_bounds__(256, 4)
-exact_small_kernel(const ExactParams p) {
-  __shared__ __align__(16) float qpatch[9 * kC3];
-  const int n = blockIdx.z;
-  const int cnt = __ldg(p.list_count + n);
-  if (cnt == 0 || cnt > kSmallMax || (int)blockIdx.y >= cnt) return;
-  const int L = p.H * p.W, lk1 = p.Hr * p.Wr, Lk = p.rf * lk1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (Lk + gridDim.x - 1) / gridDim.x;
-  const int k_lo = blockIdx.x * per, k_hi = min(Lk, k_lo + per);
-  const float* qimg = p.q32 + (size_t)n * L * kC3;
-  const float4* qv = reinterpret_cast<const float4*>(qpatch) + lane;  // tap t at qv[t * 32]
-  for (int qi = blockIdx.y; qi < cnt; qi += gridDim.y) {
-    const int q = __ldg(p.list + (size_t)n * L + qi);
-    const int y = q / p.W, x = q % p.W;
-    const float rq = __ldg(p.rq + (size_t)n * L + q);
-    __syncthreads();  // previous query's patch no longer in use
-    for (int e = threadIdx.x; e < 9 * 32; e += 256) {
-      const int t = e >> 5, l4 = e & 31;
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      const bool in = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-      reinterpret_cast<float4*>(qpatch)[e] =
-          in ? __ldg(reinterpret_cast<const float4*>(qimg + ((size_t)yy * p.W + xx) * kC3) + l4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    unsigned long long best = 0ull;
-    for (int j = k_lo + warp; j < k_hi; j += 8) {
-      const int f = j / lk1, rem = j - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
-      const float* kimg = p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3;
-      // fp32 accumulation like exact_search_kernel (the exhaustive paths agree with each other and are
-      // within ~1e-7 of the fp64 rescoring, far inside the 1e-5 near-tie rule)
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
-        if (yy >= 0 && yy < p.Hr && xx >= 0 && xx < p.Wr) {
-          const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * p.Wr + xx) * kC3) + lane);
-          const float4 qq = qv[t * 32];
-          a0 = fmaf(qq.x, kv.x, a0); a1 = fmaf(qq.y, kv.y, a1); a2 = fmaf(qq.z, kv.z, a2); a3 = fmaf(qq.w, kv.w, a3);
-        }
-      }
-      float acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
-      const unsigned long long key = pack_score(acc * rq * rk, j);
-      best = key > best ? key : best;
-    }
-    if (lane == 0 && best) atomicMax(p.packed + (size_t)n * L + q, best);
-  }
-}
-
+// clears the packed maxima, the per-item queue counters + kCnt* words and the caller's stats block
 __global__ void __launch_bounds__(256)
-clear_packed_kernel(unsigned long long* packed, int32_t* flag_count, size_t total, int n) {
+clear_packed_kernel(unsigned long long* packed, int32_t* counters, size_t total, int n, int32_t* stats) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) packed[i] = 0ull;
-  if (i < (size_t)n) flag_count[i] = 0;
+  if (i < (size_t)(n + kCntWords)) counters[i] = 0;
+  if (stats && i < (size_t)kStatsWords) stats[i] = 0;
 }
 
 // grid: (blocks, 1, n)
@@ -401,18 +318,18 @@ unpack_kernel(const unsigned long long* __restrict__ packed, const int32_t* __re
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
     const int q = list ? __ldg(list + (size_t)n * L + i) : i;
     const unsigned long long b = packed[(size_t)n * L + q];
-    const float s = unflip_f32((unsigned)(b >> 32));
-    const int j = (int)(0xffffffffu - (unsigned)(b & 0xffffffffull));
-    S[(size_t)n * L + q] = s;
+    const int j = packed_key(b);
+    S[(size_t)n * L + q] = packed_score(b);
     arg32[(size_t)n * L + q] = j;
     if (arg64) arg64[(size_t)n * L + q] = j;
   }
 }
 
-static int clear_lists(const Plan& p, char* ws, cudaStream_t st) {
+static int clear_lists(const Plan& p, char* ws, int32_t* stats, cudaStream_t st) {
   const size_t tot = (size_t)p.n * p.H * p.W;
-  clear_packed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((unsigned long long*)(ws + p.off_packed),
-                                                                      (int32_t*)(ws + p.off_counters), tot, p.n);
+  const size_t cover = tot > (size_t)(p.n + kCntWords) ? tot : (size_t)(p.n + kCntWords);
+  clear_packed_kernel<<<(unsigned)((cover + 255) / 256), 256, 0, st>>>((unsigned long long*)(ws + p.off_packed),
+                                                                        (int32_t*)(ws + p.off_counters), tot, p.n, stats);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }
@@ -426,9 +343,9 @@ static ExactParams exact_params(const Plan& p, char* ws) {
   return e;
 }
 
-int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, char* ws, cudaStream_t st) {
+int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st) {
   if (p.n > 65535) { set_error("exact search: n too large"); return SPEI_ERR_ARG; }
-  int rc = clear_lists(p, ws, st);
+  int rc = clear_lists(p, ws, stats, st);
   if (rc) return rc;
   ExactParams e = exact_params(p, ws);
   const int L = p.H * p.W, qblocks = (L + kEQ - 1) / kEQ;
@@ -447,7 +364,7 @@ int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, ch
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st) {
   if (p.n > 65535) { set_error("rescore: n too large"); return SPEI_ERR_ARG; }
-  int rc = clear_lists(p, ws, st);
+  int rc = clear_lists(p, ws, stats, st);
   if (rc) return rc;
   RescoreParams r{};
   r.n = p.n; r.rf = p.rf; r.H = p.H; r.W = p.W; r.Hr = p.Hr; r.Wr = p.Wr;
@@ -455,27 +372,28 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   r.eps = eps;
   r.q32 = (const float*)(ws + p.off_q32); r.k32 = (const float*)(ws + p.off_k32);
   r.rq = (const float*)(ws + p.off_rq); r.rk = (const float*)(ws + p.off_rk); r.qss = (const float*)(ws + p.off_qss);
+  r.dq = (const float*)(ws + p.off_dq); r.dkmax = (const int*)(ws + p.off_dkmax);
   r.cval = (const float*)(ws + p.off_cval); r.cidx = (const int32_t*)(ws + p.off_cidx);
   r.S = S; r.arg32 = arg32; r.arg64 = arg64;
-  r.flag_list = (int32_t*)(ws + p.off_flag); r.flag_count = (int32_t*)(ws + p.off_counters);
+  r.flag_list = (int32_t*)(ws + p.off_flag); r.counters = (int32_t*)(ws + p.off_counters);
+  r.thr = (float*)(ws + p.off_thr); r.packed = (unsigned long long*)(ws + p.off_packed);
   r.stats = stats;
   const long long nq = (long long)p.n * p.H * p.W;
   rescore_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(r);
   SPEI_CUDA(cudaGetLastError());
 
-  // exhaustive search for the queued queries.  The count lives on the device (no host sync): launch a
-  // grid that covers the worst case per item in chunks; blocks beyond the count exit immediately.
+  // queued queries (saturated candidate lists): second tcgen05 pass enumerating every key at or above each query's
+  // threshold, exact rescoring of what it emits.  The counts live on the device (no host sync): fixed grids, blocks
+  // beyond the count exit immediately.
+  if ((rc = launch_relevance_flagged(p, stats, ws, st))) return rc;
+  // last resort (the pass ran out of packed rows or emission slots): exhaustive fp32 search of the queued queries
   ExactParams e = exact_params(p, ws);
-  e.list = r.flag_list; e.list_count = r.flag_count;
+  e.list = r.flag_list; e.list_count = r.counters;
+  e.enable = r.counters + p.n + kCntExhaust;
   const int L = p.H * p.W, qblocks = (L + kEQ - 1) / kEQ;
   const int max_splits = (p.rf * p.Hr * p.Wr + kEK - 1) / kEK;
-  // few queries are expected here: many key splits (short serial loops), few query-block columns
-  e.key_splits = max_splits < 450 ? max_splits : 450;
-  e.small_max = kSmallMax;
-  const int key_blocks = (p.rf * p.Hr * p.Wr + 63) / 64;
-  exact_small_kernel<<<dim3(key_blocks < 296 ? key_blocks : 296, 8, p.n), 256, 0, st>>>(e);
-  SPEI_CUDA(cudaGetLastError());
-  exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
+  e.key_splits = max_splits < 148 ? max_splits : 148;
+  exact_search_kernel<<<dim3(qblocks < 16 ? qblocks : 16, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());
   unpack_kernel<<<dim3(148, 1, p.n), 256, 0, st>>>(e.packed, e.list, e.list_count, L, S, arg32, arg64);
   SPEI_CUDA(cudaGetLastError());

@@ -28,6 +28,14 @@ constexpr int kSQTileV = 4;       // query tile: 32 x 4 positions = 128 MMA rows
 constexpr int kSMaxNy = 8;        // key tile: 32 x Ny positions = up to 256 MMA columns
 constexpr int kCGS = 4;           // channel groups per key pipeline stage (32 channels = 2 x K16)
 constexpr int kStages = 6;        // key pipeline depth (1.5 key tiles in flight)
+// second tcgen05 pass over the queries whose candidate lists saturated (relevance_flagged.cu)
+constexpr int kFlagNy = 32;           // key tile: 8 x 32 positions = 256 MMA columns
+constexpr int kFlagMaxRows = 16384;   // packed query rows per call (128 tiles of 128); beyond that the exhaustive search takes over
+constexpr int kFlagMaxEmit = 1 << 20; // (query, key) pairs the pass may emit per call
+constexpr int kStatsWords = 8;        // int32 counters of spei_search_transfer / spei_rescore (include/speinet_b200.h)
+// slack added to the certified bf16-score error bound: fp32 accumulation of 1152 products in tensor memory (n * 2^-23 at
+// worst) plus the epilogue's tap-sum adds, relative to a normalised score of magnitude <= 1
+constexpr float kAccSlack = 1.6e-4f;
 
 // One operand (query set or key set) staged in (u, v) coordinates: u is the fast axis in memory.
 // orient 0: u = x, v = y.   orient 1: u = y, v = x (image transposed so the tile grid wastes less).
@@ -54,7 +62,12 @@ struct Plan {
   int maxseg;      // max key segments a query tile is split into
   // workspace offsets (bytes)
   size_t off_qbf, off_kbf, off_q32, off_k32, off_rq, off_rk, off_rkpad, off_qss, off_kss;
+  size_t off_qrs, off_krs;     // per-pixel energy of the bf16 rounding residual  sum_c (x - bf16(x))^2
+  size_t off_dq, off_dkmax;    // per-query relative residual norm of its patch; per-item maximum over the keys (float bits)
   size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag, off_ref3n, off_ref2n;
+  // second pass (relevance_flagged.cu): packed A operand, per-row threshold / query id, emitted pairs
+  size_t off_thr, off_apack, off_prow_thr, off_prow_q, off_emit_q, off_emit_k;
+  int flag_rows;               // capacity of the packed A operand in query rows (multiple of 128)
   size_t total;
 };
 
@@ -77,7 +90,14 @@ int tcs_epilogue_groups();   // candidate lists per (query, key segment) the tap
 void set_debug_acc(float* ptr);
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st);
-int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, char* ws, cudaStream_t st);
+int launch_relevance_flagged(const Plan& p, int32_t* stats, char* ws, cudaStream_t st);
+// candidate window of the bf16 pass: eps > 0 = fixed (uncertified) window in normalised relevance units; eps <= 0 = the
+// certified per-query window 2 * Delta_i (Delta_i bounds |bf16 score - exact score| for every key, from the measured rounding
+// residuals of the query patch and of the worst key patch, Cauchy-Schwarz; DESIGN.md section 4(b'))
+__host__ __device__ inline float certified_delta(float dq, float dkmax) {
+  return 1.01f * (dq + (1.f + dq) * dkmax) + kAccSlack;
+}
+int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st);
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
                        const int32_t* arg32, const float* ref, float* out, cudaStream_t st);
 int launch_stage_ref_nhwc(const float* ref, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st);
@@ -85,6 +105,10 @@ int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, 
                             const int32_t* arg32, const float* ref_nhwc, float* out, cudaStream_t st);
 int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
                       const float* weight, const float* bias, float* out, cudaStream_t st);
+// counters at workspace + off_counters (int32): [0, n) queries queued per item for the second pass; then
+constexpr int kCntEmit = 0;       // + n: pairs emitted by the second pass
+constexpr int kCntExhaust = 1;    // + n: != 0 -> capacity exceeded, the queued queries take the exhaustive fp32 search
+constexpr int kCntWords = 8;
 
 int launch_rl_deconv(int n, int c, int h, int w, int ks, int iters, float lambda, const float* img, const float* kern, float* out,
                      cudaStream_t st);

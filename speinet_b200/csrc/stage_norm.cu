@@ -8,6 +8,10 @@
 //         halo tile in shared memory.
 //   * x32 [img][H][W][128] fp32 (NHWC)   -- read by the exact fp32 rescoring with 512-byte rows.
 //   * r   [img][H*W] fp32                -- 1 / max(||3x3x128 patch||_2, 1e-12)  (F.normalize, :30-31)
+//   * d   [img][H*W] fp32 (queries) / dkmax [item] (keys: maximum) -- ||patch - bf16(patch)||_2 / ||patch||_2, the measured
+//         relative rounding residual of the patch.  By Cauchy-Schwarz the bf16 score of (query i, key j) is within
+//         d_i + (1 + d_i) d_j of the exact normalised relevance: the candidate window of the tcgen05 pass and the
+//         rescoring threshold are derived from these numbers instead of from an assumed worst case (certified_delta()).
 //   * rkpad (keys) [img][tv*Ny][tu*8] (dense) or [img][tv*Ny][Upad] (tap-sharing, u border included)
 //         -- r in tile-padded (u,v) order, NaN for padded positions so
 //         that a padded key can never win a comparison in the relevance epilogue.
@@ -23,7 +27,11 @@ struct StageOp {
   __nv_bfloat16* bf;       // [nimg][16][Vpad][Upad][8]
   float* x32;              // [nimg][H][W][128]
   float* ss;               // [nimg][H][W] per-pixel sum of squares
+  float* rs;               // [nimg][H][W] per-pixel sum of squared bf16 rounding residuals
   float* r;                // [nimg][H*W] reciprocal patch norms
+  float* d;                // queries: [nimg][H*W] relative residual norm of the patch (else nullptr)
+  int* dmax;               // keys: [nimg / frames] maximum relative residual norm over the item's keys, as float bits (else nullptr)
+  int frames;              // images per item (1 for queries, rf for keys)
   float* rkpad;            // keys only (else nullptr): tile-padded reciprocal norms, NaN outside the image
   int nimg, H, W, orient, U, V, Upad, Vpad;
   int UT, VT, border;      // rkpad geometry
@@ -35,6 +43,7 @@ __global__ void __launch_bounds__(256)
 stage_transpose_kernel(const StageOp oq, const StageOp ok) {
   __shared__ float tile[kC3][kPx + 1];
   __shared__ float part[8][kPx];
+  __shared__ float partr[8][kPx];
   const bool is_k = (int)blockIdx.z >= oq.nimg;
   const StageOp& o = is_k ? ok : oq;
   const int img = is_k ? blockIdx.z - oq.nimg : blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kPx;
@@ -78,21 +87,28 @@ stage_transpose_kernel(const StageOp oq, const StageOp ok) {
   // per-pixel sum of squares over the 128 channels (fixed order: 8 partials of 16 channels)
   {
     const int px = lane, pt = warp;
-    float s = 0.f;
+    float s = 0.f, sr = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const float a = tile[pt * 16 + i][px]; s = fmaf(a, a, s); }
+    for (int i = 0; i < 16; ++i) {
+      const float a = tile[pt * 16 + i][px];
+      s = fmaf(a, a, s);
+      const float res = a - __bfloat162float(__float2bfloat16_rn(a));   // exact: the operand the tensor cores see differs by this
+      sr = fmaf(res, res, sr);
+    }
     part[pt][px] = s;
+    partr[pt][px] = sr;
   }
   __syncthreads();
   if (warp == 0 && in) {
-    float s = 0.f;
+    float s = 0.f, sr = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += part[i][lane];
+    for (int i = 0; i < 8; ++i) { s += part[i][lane]; sr += partr[i][lane]; }
     ss[(size_t)img * plane + (size_t)y * W + x0 + lane] = s;
+    o.rs[(size_t)img * plane + (size_t)y * W + x0 + lane] = sr;
   }
 }
 
-__device__ __forceinline__ float patch_rnorm(const float* __restrict__ ss, int H, int W, int y, int x) {
+__device__ __forceinline__ float patch_sum(const float* __restrict__ ss, int H, int W, int y, int x) {
   float s = 0.f;
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy)
@@ -101,7 +117,10 @@ __device__ __forceinline__ float patch_rnorm(const float* __restrict__ ss, int H
       const int yy = y + dy, xx = x + dx;
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) s += __ldg(ss + (size_t)yy * W + xx);
     }
-  return 1.0f / fmaxf(sqrtf(s), 1e-12f);  // F.normalize: v / max(||v||, eps)
+  return s;
+}
+__device__ __forceinline__ float patch_rnorm(const float* __restrict__ ss, int H, int W, int y, int x) {
+  return 1.0f / fmaxf(sqrtf(patch_sum(ss, H, W, y, x)), 1e-12f);  // F.normalize: v / max(||v||, eps)
 }
 
 // rq, rk and the tile-padded key norms in ONE launch: thread i covers [q positions | k positions | padded k positions]
@@ -115,7 +134,13 @@ patch_norms_kernel(const StageOp oq, const StageOp ok) {
     if (i >= nq) i -= nq;
     const size_t plane = (size_t)o.H * o.W;
     const int img = (int)(i / plane), rem = (int)(i % plane);
-    o.r[i] = patch_rnorm(o.ss + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
+    const float s = patch_sum(o.ss + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
+    o.r[i] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    // relative rounding residual of the patch, rounded up (1 + 2^-20 covers the fp32 sums, sqrt and division above)
+    const float sr = patch_sum(o.rs + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
+    const float dl = s > 0.f ? fminf(sqrtf(sr / s) * 1.000001f, 1.f) : 0.f;
+    if (o.d) o.d[i] = dl;
+    if (o.dmax) atomicMax(o.dmax + img / o.frames, __float_as_int(dl));   // non-negative floats order like their bit patterns
     return;
   }
   i -= nq + nk;
@@ -135,6 +160,8 @@ patch_norms_kernel(const StageOp oq, const StageOp ok) {
 __global__ void __launch_bounds__(256)
 zero_padding_kernel(const StageOp oq, const StageOp ok) {
   const StageOp& o = blockIdx.z ? ok : oq;
+  if (blockIdx.z == 1 && blockIdx.x == 0)   // per-item key maxima start at 0 (patch_norms_kernel runs two launches later)
+    for (int i = threadIdx.x; i < ok.nimg / ok.frames; i += blockDim.x) ok.dmax[i] = 0;
   const int full_rows = o.Vpad - o.V, side_cols = o.Upad - o.U;
   const int n_full = full_rows * o.Upad, n_side = o.V * side_cols;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,10 +181,10 @@ zero_padding_kernel(const StageOp oq, const StageOp ok) {
   for (int pl = 0; pl < o.nimg * kCG; ++pl) *reinterpret_cast<uint4*>(o.bf + (pl * per + pos) * 8) = z;
 }
 
-static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* r,
-                       float* rkpad) {
+static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* rs,
+                       float* r, float* rkpad, float* d, int* dmax, int frames) {
   StageOp s{};
-  s.x = x; s.bf = bf; s.x32 = x32; s.ss = ss; s.r = r; s.rkpad = rkpad;
+  s.x = x; s.bf = bf; s.x32 = x32; s.ss = ss; s.rs = rs; s.r = r; s.rkpad = rkpad; s.d = d; s.dmax = dmax; s.frames = frames;
   s.nimg = nimg; s.H = H; s.W = W; s.orient = o.orient; s.U = o.U; s.V = o.V; s.Upad = o.Upad; s.Vpad = o.Vpad;
   // dense tiling: [tv*Ny][tu*8]; tap-sharing tiling: [tv*Ny][Upad] with the staged image's 1-position u border
   const bool shared = o.tile_u == kSTileU;
@@ -167,9 +194,11 @@ static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan
 
 int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st) {
   const StageOp oq = make_op(q, p.n, p.H, p.W, p.q, (__nv_bfloat16*)(ws + p.off_qbf), (float*)(ws + p.off_q32),
-                             (float*)(ws + p.off_qss), (float*)(ws + p.off_rq), nullptr);
+                             (float*)(ws + p.off_qss), (float*)(ws + p.off_qrs), (float*)(ws + p.off_rq), nullptr,
+                             (float*)(ws + p.off_dq), nullptr, 1);
   const StageOp ok = make_op(k, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
-                             (float*)(ws + p.off_kss), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad));
+                             (float*)(ws + p.off_kss), (float*)(ws + p.off_krs), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad),
+                             nullptr, (int*)(ws + p.off_dkmax), p.rf);
   if ((long long)oq.nimg + ok.nimg > 65535) { set_error("stage_norm: too many images"); return SPEI_ERR_ARG; }
   const int padq = (oq.Vpad - oq.V) * oq.Upad + oq.V * (oq.Upad - oq.U), padk = (ok.Vpad - ok.V) * ok.Upad + ok.V * (ok.Upad - ok.U);
   zero_padding_kernel<<<dim3(((padq > padk ? padq : padk) + 255) / 256, 1, 2), 256, 0, st>>>(oq, ok);

@@ -31,6 +31,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded waits: a protocol bug (or a dead producer) must surface as an error, never as a hung GPU and never as
+// silently wrong results.  After ~2 s (4e9 cycles) the waiter records which barrier starved in *error_flag (when the
+// launch has one) and executes `trap`: the launch fails, every later CUDA call of the process returns the error, and the
+// Python wrappers raise.  (-DSPEI_WATCHDOG_DRAIN, debug builds only: instead of trapping, every wait of the grid returns
+// immediately once the flag is set, so the kernel drains with garbage results and spei_debug_error_flag can read the word.)
+static __device__ __noinline__ void mbar_timeout(int* error_flag, uint32_t bar) {
+  if (error_flag) atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
+#ifndef SPEI_WATCHDOG_DRAIN
+  __threadfence_system();
+  __trap();
+#endif
+}
+__device__ __forceinline__ bool mbar_drained(const int* error_flag) {
+#ifdef SPEI_WATCHDOG_DRAIN
+  return error_flag && *reinterpret_cast<const volatile int*>(error_flag) != 0;
+#else
+  (void)error_flag;
+  return false;
+#endif
+}
+constexpr long long kWatchdogCycles = 4000000000ll;
+
 // Pure polling wait (mbarrier.test_wait never suspends the thread): for fine-grained producer/consumer hand-offs
 // where the wake-up latency of a suspended try_wait would dominate the stage time.
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int* error_flag) {
@@ -48,11 +70,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, in
         : "memory");
     if (ok) return;
     if ((++spins & 0xfffu) == 0) {
-      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
-      if (clock64() - t0 > 4000000000ll) {
-        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
-        return;
-      }
+      if (mbar_drained(error_flag)) return;
+      if (clock64() - t0 > kWatchdogCycles) { mbar_timeout(error_flag, bar); return; }
     }
   }
 }
@@ -77,11 +96,8 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, 
   uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if ((++spins & 0xfu) == 0) {
-      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
-      if (clock64() - t0 > 4000000000ll) {
-        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
-        return;
-      }
+      if (mbar_drained(error_flag)) return;
+      if (clock64() - t0 > kWatchdogCycles) { mbar_timeout(error_flag, bar); return; }
     }
   }
 }
@@ -95,20 +111,14 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float a0, float a1, 
       : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3 on sm_100
-// Bounded wait: a protocol bug must surface as an error code, not as a hung GPU.  On a ~2 s timeout the
-// waiter records which barrier starved in *error_flag; from then on every wait in the grid returns
-// immediately, so the kernel drains (with garbage results) and the host can read the code back.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ffu) == 0) {
-      if (*reinterpret_cast<volatile int*>(error_flag) != 0) return;
-      if (clock64() - t0 > 4000000000ll) {
-        atomicCAS(error_flag, 0, 0x10000 | (int)(bar & 0xffff));
-        return;
-      }
+      if (mbar_drained(error_flag)) return;
+      if (clock64() - t0 > kWatchdogCycles) { mbar_timeout(error_flag, bar); return; }
     }
   }
 }

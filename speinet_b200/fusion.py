@@ -21,10 +21,11 @@ from .search_transfer import SearchTransfer, SelfTransfer, _check_inputs, _ptr
 
 
 def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
-               scale: int) -> torch.Tensor:
+               scale: int, out: torch.Tensor = None) -> torch.Tensor:
     """dec + conv1x1(cat(dec, t); weight, bias) * bicubic_up(S, scale), scale in {1, 2, 4}.
 
-    dec, t: [N, C, scale*h, scale*w]; S: [N, 1, h, w]; weight: Conv2d(2C -> C, 1x1).weight; bias: [C]."""
+    dec, t: [N, C, scale*h, scale*w]; S: [N, 1, h, w]; weight: Conv2d(2C -> C, 1x1).weight; bias: [C].
+    `out`: optional preallocated contiguous fp32 result buffer (persistent buffers of a pipeline / CUDA graph)."""
     lib = _lib.load()
     out_dtype = dec.dtype
     dec_f, t_f, S_f = dec.float().contiguous(), t.float().contiguous(), S.float().contiguous()
@@ -36,8 +37,13 @@ def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torc
     if (hs, ws) != (h * scale, w * scale) or t_f.shape != dec_f.shape or tuple(w_f.shape) != (c, 2 * c):
         raise RuntimeError(f"fuse_level: inconsistent shapes dec={tuple(dec.shape)} t={tuple(t.shape)} "
                            f"S={tuple(S.shape)} weight={tuple(weight.shape)} scale={scale}")
+    if w_f.data_ptr() % 16:
+        w_f = w_f.clone()
     with torch.cuda.device(dec_f.device):
-        out = torch.empty_like(dec_f)
+        if out is None:
+            out = torch.empty_like(dec_f)
+        elif out.shape != dec_f.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dec_f.device:
+            raise RuntimeError(f"fuse_level: out must be a contiguous fp32 tensor of shape {tuple(dec_f.shape)} on {dec_f.device}")
         stream = ctypes.c_void_p(torch.cuda.current_stream(dec_f.device).cuda_stream)
         rc = lib.spei_fuse_level(n, c, h, w, scale, _ptr(dec_f), _ptr(t_f), _ptr(S_f), _ptr(w_f), _ptr(b_f), _ptr(out), stream)
         _lib.check(rc, "spei_fuse_level")

@@ -14,6 +14,7 @@ silently detaching (the reference is differentiable).
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Sequence, Union
 
 import torch
@@ -57,26 +58,51 @@ def workspace_bytes(shape: _lib.SpeiShape) -> int:
     return int(n.value)
 
 
-DEFAULT_EPS = 2e-3   # candidate window of the bf16 pass when eps <= 0 (api.cu)
+class _WorkspaceCache:
+    """One scratch buffer per (device, size), reused across calls: the caching allocator would otherwise hand a fresh
+    ~190 MB block (720p) to every call.  Reuse is stream-ordered; a call on a different stream first waits for the event
+    recorded after the previous use."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._slots = {}
+
+    def get(self, dev: torch.device, nbytes: int, stream: torch.cuda.Stream):
+        key = (dev.index, nbytes)
+        with self._lock:
+            slot = self._slots.get(key)
+            if slot is None:
+                if len(self._slots) >= 4:           # keep at most a few shapes alive
+                    self._slots.pop(next(iter(self._slots)))
+                slot = self._slots[key] = {"buf": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev), "event": None, "stream": None}
+        # (inside a CUDA-graph capture the buffer is used in capture order on the capturing stream: no event traffic)
+        if slot["event"] is not None and slot["stream"] != stream.cuda_stream and not torch.cuda.is_current_stream_capturing():
+            stream.wait_event(slot["event"])
+        return slot
+
+    @staticmethod
+    def release(slot, stream: torch.cuda.Stream):
+        if torch.cuda.is_current_stream_capturing():
+            return
+        ev = slot["event"] or torch.cuda.Event()
+        ev.record(stream)
+        slot["event"], slot["stream"] = ev, stream.cuda_stream
+
+
+_WS = _WorkspaceCache()
 
 
 def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: TensorOrList = None,
                     ref_lv2: TensorOrList = None, ref_lv3: TensorOrList = None, *, fold_mode: str = "cuda",
-                    search: str = "tcs", eps: float = 0.0, verify_window: bool = False):
-    """Functional form.  Returns (S, T_lv3, T_lv2, T_lv1, arg[int64 N x L], stats[int32 x 4]).
+                    search: str = "tcs", eps: float = 0.0, out: dict = None):
+    """Functional form.  Returns (S, T_lv3, T_lv2, T_lv1, arg[int64 N x L], stats[int32 x 8]).
     Pyramid levels passed as None are skipped (their T is None).
 
-    `verify_window`: the bf16 pass nominates every key within `eps` of a query's best bf16 score; that is exact as long
-    as no bf16 score is further than eps/2 from its exact value.  The rescoring measures the largest such deviation it
-    sees (stats[2]); with verify_window=True the wrapper reads it back (one host sync) and, if it exceeds 40 % of eps,
-    repeats the call with the rigorous window 2^-7 (worst case of bf16 rounding, ~10-30 ms at 720p).  Default off: the
-    measured maximum over all round-1 inputs is 6.3e-4 against eps/2 = 1e-3."""
-    if verify_window and search != "exact":
-        out = search_transfer(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, fold_mode=fold_mode, search=search, eps=eps)
-        eff = eps if eps > 0 else DEFAULT_EPS
-        if eff < 2.0 ** -7 and float(out[5][2].item()) * 1e-9 > 0.4 * eff:
-            out = search_transfer(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, fold_mode=fold_mode, search=search, eps=2.0 ** -7)
-        return out
+    `eps` <= 0 (default): certified candidate window -- the bf16 tensor-core pass and the exact rescoring bracket the
+    argmax with an error bound measured on the actual operands (include/speinet_b200.h, SpeiShape.eps); stats[6] counts
+    violations of that bound (always 0; `SearchTransfer.check_certificate()` raises otherwise).  `eps` > 0: fixed window.
+    `out`: optional dict of preallocated fp32 outputs {"S", "T3", "T2", "T1", "arg", "stats"} to write into (persistent
+    buffers of a pipeline / CUDA graph); missing entries are allocated."""
     lib = _lib.load()
     out_dtype = lrsr_lv3.dtype
     q = lrsr_lv3.float().contiguous()
@@ -93,25 +119,36 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
     for t, c, s, nm in ((r3, c3, 1, "ref_lv3"), (r2, c3 // 2, 2, "ref_lv2"), (r1, c3 // 4, 4, "ref_lv1")):
         if t is not None and tuple(t.shape) != (n, rf, c, s * hr, s * wr):
             raise RuntimeError(f"{nm}: expected {(n, rf, c, s * hr, s * wr)}, got {tuple(t.shape)}")
+    # the C-ABI wants 16-byte aligned bases (TMA / vector loads): a contiguous view at an odd storage offset is cloned
+    q, k, r1, r2, r3 = (t.clone() if t is not None and t.data_ptr() % 16 else t for t in (q, k, r1, r2, r3))
     shape = _lib.SpeiShape(n=n, h=h, w=w, hr=hr, wr=wr, rf=rf, c3=c3, c2=c3 // 2, c1=c3 // 4,
                            fold_mode=_FOLD[fold_mode], search=_SEARCH[search], eps=float(eps))
     dev = q.device
+    out = out or {}
+
+    def buf(name, shp, dtype=torch.float32):
+        t = out.get(name)
+        if t is None:
+            return torch.empty(shp, dtype=dtype, device=dev)
+        if tuple(t.shape) != tuple(shp) or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+            raise RuntimeError(f"out[{name!r}]: expected a contiguous {dtype} tensor of shape {tuple(shp)} on {dev}")
+        return t
     with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
         ws_bytes = workspace_bytes(shape)
-        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
-        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-        S = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
-        T3 = torch.empty((n, c3, h, w), dtype=torch.float32, device=dev) if r3 is not None else None
-        T2 = torch.empty((n, c3 // 2, 2 * h, 2 * w), dtype=torch.float32, device=dev) if r2 is not None else None
-        T1 = torch.empty((n, c3 // 4, 4 * h, 4 * w), dtype=torch.float32, device=dev) if r1 is not None else None
-        arg = torch.empty((n, h * w), dtype=torch.int64, device=dev)
-        stats = torch.empty(4, dtype=torch.int32, device=dev)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        slot = _WS.get(dev, ws_bytes, cur)
+        ws_ptr = (slot["buf"].data_ptr() + 255) // 256 * 256
+        S = buf("S", (n, 1, h, w))
+        T3 = buf("T3", (n, c3, h, w)) if r3 is not None else None
+        T2 = buf("T2", (n, c3 // 2, 2 * h, 2 * w)) if r2 is not None else None
+        T1 = buf("T1", (n, c3 // 4, 4 * h, 4 * w)) if r1 is not None else None
+        arg = buf("arg", (n, h * w), torch.int64)
+        stats = buf("stats", (_lib.STATS_WORDS,), torch.int32)
         rc = lib.spei_search_transfer(ctypes.byref(shape), _ptr(q), _ptr(k), _ptr(r1), _ptr(r2), _ptr(r3), _ptr(S),
                                       _ptr(T3), _ptr(T2), _ptr(T1), _ptr(arg), _ptr(stats), ctypes.c_void_p(ws_ptr),
-                                      ctypes.c_size_t(ws_bytes), stream)
+                                      ctypes.c_size_t(ws_bytes), ctypes.c_void_p(cur.cuda_stream))
         _lib.check(rc, "spei_search_transfer")
-        ws.record_stream(torch.cuda.current_stream(dev))
+        _WS.release(slot, cur)
     if out_dtype != torch.float32:  # bf16 / fp16 callers get their dtype back; arithmetic stayed fp32
         S, T3, T2, T1 = (t.to(out_dtype) if t is not None else None for t in (S, T3, T2, T1))
     return S, T3, T2, T1, arg, stats
@@ -120,16 +157,14 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
 class SearchTransfer(nn.Module):
     """Same surface as the reference class (SearchTransfer.py:7-51)."""
 
-    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tcs", eps: float = 0.0,
-                 verify_window: bool = False):
+    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tcs", eps: float = 0.0):
         super().__init__()
-        self.verify_window = verify_window
         # never used in forward, exactly as in the reference (:10-11); kept for strict checkpoint loading
         self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
         self.search2 = nn.Conv2d(n_feat * 2, n_feat, kernel_size=1, stride=1, padding=0)
         self.fold_mode, self.search, self.eps = fold_mode, search, eps
         self.last_index = None   # R_lv3_star_arg of the last call, int64 [N, H*W]
-        self.last_stats = None   # int32 [4] device counters (see include/speinet_b200.h)
+        self.last_stats = None   # int32 [8] device counters (see include/speinet_b200.h)
 
     def bis(self, input, dim, index):
         """Batch index select, kept for API compatibility (SearchTransfer.py:12-22):
@@ -142,12 +177,22 @@ class SearchTransfer(nn.Module):
 
     def forward(self, lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, return_index: bool = False):
         S, T3, T2, T1, arg, stats = search_transfer(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3,
-                                                     fold_mode=self.fold_mode, search=self.search, eps=self.eps,
-                                                     verify_window=self.verify_window)
+                                                     fold_mode=self.fold_mode, search=self.search, eps=self.eps)
         self.last_index, self.last_stats = arg, stats
         if return_index:
             return S, T3, T2, T1, arg
         return S, T3, T2, T1
+
+    def check_certificate(self) -> dict:
+        """Host-side check of the last call's counters (one device sync): raises if the certified error bound of the bf16
+        pass was violated for any rescored candidate (stats[6] != 0).  Returns the counters by name."""
+        if self.last_stats is None:
+            raise RuntimeError("no call yet")
+        st = dict(zip(_lib.STATS_NAMES, self.last_stats.cpu().tolist()))
+        if st["certified_bound_violations"]:
+            raise RuntimeError(f"bf16 score error bound violated for {st['certified_bound_violations']} candidates: "
+                               "the argmax of the last call is not certified")
+        return st
 
 
 class SelfTransfer(nn.Module):

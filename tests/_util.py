@@ -94,7 +94,7 @@ def expected_debug_tile_tcs(q, k, info):
 
 def run_search(q, k, search=_lib.SEARCH_TCS, eps=0.0):
     """Stage + relevance only, through the C-ABI.  q [N,128,H,W], k [N,Rf,128,Hr,Wr] CUDA fp32.
-    Returns (S [N,1,H,W], arg32 [N,L], stats[4], error_flag)."""
+    Returns (S [N,1,H,W], arg32 [N,L], stats[8], error_flag)."""
     lib = _lib.load()
     n, _, h, w = q.shape
     _, rf, _, hr, wr = k.shape
@@ -102,7 +102,7 @@ def run_search(q, k, search=_lib.SEARCH_TCS, eps=0.0):
     ws, ptr, nbytes = alloc_workspace(shape)
     S = torch.empty((n, 1, h, w), device="cuda")
     arg32 = torch.empty((n, h * w), dtype=torch.int32, device="cuda")
-    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(_lib.STATS_WORDS, dtype=torch.int32, device="cuda")
     st = cur_stream()
     _lib.check(lib.spei_stage_norm(ctypes.byref(shape), vp(q), vp(k), ctypes.c_void_p(ptr), nbytes, st), "stage_norm")
     _lib.check(lib.spei_relevance_argmax(ctypes.byref(shape), vp(S), vp(arg32), ctypes.c_void_p(0), vp(stats),

@@ -281,7 +281,7 @@ def stage_time720():
     ws, ptr, nbytes = U.alloc_workspace(shape)
     S = torch.empty(1, 1, h, w, device="cuda")
     arg32 = torch.empty(1, h * w, dtype=torch.int32, device="cuda")
-    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
     st = U.cur_stream()
     wsp = ctypes.c_void_p(ptr)
     REC["workspace_MB"] = nbytes / 1e6

@@ -35,7 +35,7 @@ def assert_indices_agree(q, k_list, got, want):
 
 def test_library_is_the_native_one():
     lib = speinet_b200.load_library()
-    assert lib.spei_version() == 100
+    assert lib.spei_version() == _lib.VERSION
     info = U.plan_info(U.make_shape(1, 180, 320, 180, 320))
     assert info["num_sms"] >= 100 and info["G"] == info["num_sms"]
 
@@ -381,19 +381,59 @@ def test_fusion_small_and_partial_tiles_vs_oracle(hw):
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
 
 
-def test_verify_window_repeats_with_the_rigorous_window():
-    """A deliberately tiny eps makes the measured bf16 deviation exceed 40 % of the window: verify_window=True must
-    notice (stats[2]) and fall back to the rigorous 2^-7 window; the result then agrees with the exhaustive fp32 search."""
+def test_fixed_window_mode_and_its_deviation_counter():
+    """eps > 0 selects the fixed (uncertified) window of round 1: with a deliberately tiny eps the measured bf16 deviation
+    (stats[2]) exceeds half the window -- the situation the certified default exists for -- while the default call on the
+    same inputs agrees with the exhaustive fp32 search and reports no bound violation."""
     rng = np.random.default_rng(31)
     q = (rng.standard_normal((1, 128, 20, 28)) * 0.2).astype(np.float32)
     k = (rng.standard_normal((1, 128, 20, 28)) * 0.04).astype(np.float32)
     exact = speinet_b200.search_transfer(cu(q), cu(k), search="exact")
     tiny = speinet_b200.search_transfer(cu(q), cu(k), eps=2e-5)
-    assert float(tiny[5][2].item()) * 1e-9 > 0.4 * 2e-5            # the window really was too tight for bf16
-    safe = speinet_b200.search_transfer(cu(q), cu(k), eps=2e-5, verify_window=True)
+    assert float(tiny[5][2].item()) * 1e-9 > 0.5 * 2e-5            # the window really was too tight for bf16
+    safe = speinet_b200.search_transfer(cu(q), cu(k))
     assert_indices_agree(q, [k], safe[4].cpu().numpy(), exact[4].cpu().numpy())
     np.testing.assert_allclose(safe[0].cpu().numpy(), exact[0].cpu().numpy(), rtol=RTOL_S, atol=1e-6)
-    assert int(safe[5][1].item()) > int(tiny[5][1].item())        # more candidates were rescored in the second pass
+    st = safe[5].cpu().tolist()
+    assert st[6] == 0 and st[3] == 0
+    assert st[1] >= int(tiny[5][1].item())                          # the certified window rescores at least as many candidates
+
+
+@pytest.mark.parametrize("search", TC_MODES)
+def test_certified_bound_holds_and_second_pass_handles_saturated_lists(search):
+    """A constant feature vector + 20 % noise: ~240 keys per query sit within the certified window, every candidate list saturates,
+    and the second tcgen05 pass (relevance_flagged.cu) must enumerate them.  The result still equals the exhaustive fp32
+    search; stats: saturated queries > 0, pairs emitted > 0, no capacity fallback, zero bound violations."""
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((1, 128, 1, 1)).astype(np.float32)
+    q = (base + 0.2 * rng.standard_normal((1, 128, 33, 47))).astype(np.float32)
+    k = (base + 0.2 * rng.standard_normal((1, 2, 128, 29, 41))).astype(np.float32)
+    S0, a0, _, f0 = U.run_search(cu(q), cu(k), search=_lib.SEARCH_EXACT)
+    S1, a1, st1, f1 = U.run_search(cu(q), cu(k), search=SEARCH_MODES[search])
+    st = st1.cpu().tolist()
+    assert f0 == 0 and f1 == 0
+    assert st[0] > 1000 and st[5] >= 16 * st[0] and st[3] == 0 and st[6] == 0, st
+    diff = a0 != a1
+    if diff.any():
+        assert float((S0.reshape(1, -1)[diff] - S1.reshape(1, -1)[diff]).abs().max()) < 1e-5
+    torch.testing.assert_close(S1, S0, rtol=RTOL_S, atol=1e-6)
+
+
+def test_second_pass_capacity_overflow_falls_back_to_exhaustive_search():
+    """A constant image: every key is inside every query's window, the second pass would have to emit L x Lk pairs.  The
+    emission buffer overflows, the device flag routes the queued queries to the exhaustive fp32 search, and the reference
+    semantics survive: every relevance equal -> first index (torch.max), S = 1."""
+    q = torch.full((1, 128, 40, 64), 0.25, device="cuda")
+    k = torch.full((1, 1, 128, 24, 50), 0.5, device="cuda")
+    q[0, :, 0, 0] += 0.001   # keep the borders from being the unique best
+    S, a, st, flag = U.run_search(q, k)
+    S0, a0, _, _ = U.run_search(q, k, search=_lib.SEARCH_EXACT)
+    st = st.cpu().tolist()
+    assert flag == 0 and st[3] != 0 and st[6] == 0, st
+    diff = a != a0
+    if diff.any():
+        assert float((S.reshape(1, -1)[diff] - S0.reshape(1, -1)[diff]).abs().max()) < 1e-5
+    torch.testing.assert_close(S, S0, rtol=RTOL_S, atol=1e-6)
 
 
 # ------------------------------------------------------------------ (f-1 / f-3) resize + 1x1 conv + ReLU chains

@@ -120,3 +120,54 @@ def test_gather_rows_world2_gloo():
         for r in range(world):
             for got, s in zip(ret[r], (1, 1, 2, 4)):
                 assert got == rows.repeat_interleave(s).tolist()
+
+
+def test_install_on_the_real_reference_speinet_swaps_modules_and_keeps_checkpoint_keys():
+    """`install()` against the reference's own `SPEINet` class (speinet.py:53-54, 81, 129), imported behind the shims of
+    SURVEY.md section 8(c): the two transfer modules are replaced by this package's, `_decode` is rebound, the module
+    global `r_l_per_channel` of model/speinet.py points at the CUDA edge prior, and the state-dict keys / values are
+    untouched (a strict checkpoint load before or after keeps working).  Mechanics only: no forward pass without a GPU."""
+    import importlib.util
+    import sys
+    import types
+    ref = os.environ.get("SPEINET_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "model")):
+        pytest.skip("reference not mounted")
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mk_golden_model", os.path.join(here, "golden", "make_golden_model.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    mk.install_shims()
+    env_before = os.environ.get("CUDA_VISIBLE_DEVICES")
+    saved_modules = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.")}
+    sys.path.insert(0, ref)
+    try:
+        from model import speinet as ref_speinet  # sets CUDA_VISIBLE_DEVICES at import (rcl.py:16)
+        args = types.SimpleNamespace(patch_size=64, window_size=4, rgb_range=1, depths=[2] * 2, embed_dim=64, num_heads=[4] * 2,
+                                     mlp_ratio=2, resi_connection="1conv", n_colors=3, n_sequence=3, n_resblock=1, n_feat=32, cpu=True)
+        net = ref_speinet.SPEINet(in_channels=3, n_sequence=3, out_channels=3, n_resblock=1, n_feat=32, device="cpu", args=args).eval()
+        sd_before = {k: v.clone() for k, v in net.state_dict().items()}
+        ref_st_cls, ref_rl = type(net.SearchTransfer), ref_speinet.r_l_per_channel
+        assert ref_st_cls.__module__.startswith("model.")
+        speinet_b200.install(net)
+        assert isinstance(net.SearchTransfer, speinet_b200.SearchTransfer) and isinstance(net.SelfTransfer, speinet_b200.SelfTransfer)
+        assert net._decode.__func__ is speinet_b200.decode_fused
+        assert ref_speinet.r_l_per_channel is speinet_b200.r_l_per_channel and ref_rl is not speinet_b200.r_l_per_channel
+        sd_after = net.state_dict()
+        assert list(sd_after) == list(sd_before)
+        assert all(torch.equal(sd_after[k], sd_before[k]) for k in sd_before)
+        net.load_state_dict(sd_before, strict=True)                       # inference_SPEINet.py:232 loads strict
+        # the call site speinet.py:135 passes five positional tensors and unpacks four results
+        import inspect
+        params = list(inspect.signature(net.SearchTransfer.forward).parameters)
+        assert params[:5] == ["lrsr_lv3", "refsr_lv3", "ref_lv1", "ref_lv2", "ref_lv3"]
+        ref_speinet.r_l_per_channel = ref_rl
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_modules)
+        if env_before is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = env_before

@@ -15,7 +15,7 @@ shape = U.make_shape(1, h, w, h, w)
 ws, ptr, nbytes = U.alloc_workspace(shape)
 st = U.cur_stream(); wsp = ctypes.c_void_p(ptr)
 S = torch.empty(1, 1, h, w, device="cuda"); arg32 = torch.empty(1, h * w, dtype=torch.int32, device="cuda")
-stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+stats = torch.zeros(8, dtype=torch.int32, device="cuda")
 stage = lambda: _lib.check(lib.spei_stage_norm(ctypes.byref(shape), U.vp(q), U.vp(k), wsp, nbytes, st), "stage")
 stage()
 _lib.check(lib.spei_relevance_candidates(ctypes.byref(shape), wsp, nbytes, st), "cand")
