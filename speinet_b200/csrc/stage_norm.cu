@@ -136,11 +136,17 @@ patch_norms_kernel(const StageOp oq, const StageOp ok) {
     const int img = (int)(i / plane), rem = (int)(i % plane);
     const float s = patch_sum(o.ss + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
     o.r[i] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
-    // relative rounding residual of the patch, rounded up (1 + 2^-20 covers the fp32 sums, sqrt and division above)
+    // relative rounding residual of the patch (the 1 % factor of certified_delta() covers the fp32 sums, sqrt and division)
     const float sr = patch_sum(o.rs + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
-    const float dl = s > 0.f ? fminf(sqrtf(sr / s) * 1.000001f, 1.f) : 0.f;
+    const float dl = s > 0.f ? fminf(sqrtf(sr / s), 1.f) : 0.f;
     if (o.d) o.d[i] = dl;
-    if (o.dmax) atomicMax(o.dmax + img / o.frames, __float_as_int(dl));   // non-negative floats order like their bit patterns
+    if (o.dmax) {
+      // per-item maximum: one atomic per run of lanes that share the item (non-negative floats order like their bit patterns)
+      const int item = img / o.frames;
+      const unsigned peers = __match_any_sync(__activemask(), item);
+      const int mx = __reduce_max_sync(peers, __float_as_int(dl));
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMax(o.dmax + item, mx);
+    }
     return;
   }
   i -= nq + nk;

@@ -21,29 +21,50 @@ def shard_clips(num_clips: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_clips, world))
 
 
-def gather_outputs(local: torch.Tensor, num_clips: int, rank: int, world: int, group=None) -> torch.Tensor:
+class _PendingGather:
+    """Handle of an asynchronous `gather_outputs`: `result()` waits for the collective (stream-side) and returns the
+    [num_clips, ...] tensor in clip order."""
+
+    def __init__(self, work, recv, send, num_clips, world, per, tail):
+        self.work, self.recv, self.send = work, recv, send
+        self.num_clips, self.world, self.per, self.tail = num_clips, world, per, tail
+
+    def result(self) -> torch.Tensor:
+        if self.work is not None:
+            self.work.wait()
+        recv = self.recv.view((self.world, self.per) + tuple(self.tail))
+        out = recv.new_empty((self.num_clips,) + tuple(self.tail))
+        for r in range(self.world):
+            ids = shard_clips(self.num_clips, r, self.world)
+            if ids:
+                out[ids] = recv[r, :len(ids)]
+        return out
+
+
+def gather_outputs(local: torch.Tensor, num_clips: int, rank: int, world: int, group=None, async_op: bool = False):
     """All-gather per-clip outputs back into clip order.
 
     `local` is [len(shard_clips(num_clips, rank, world)), ...]; the result is [num_clips, ...] on every
-    rank.  Ragged shards are padded to the longest shard for the collective and trimmed afterwards."""
+    rank.  Ragged shards are padded to the longest shard for the collective and trimmed afterwards.
+    With `async_op` the collective is only enqueued (NCCL's stream waits for the producer of `local`, the caller's
+    stream does not wait for NCCL) and a handle is returned whose `result()` completes it -- the gather of clip i then
+    overlaps the kernels of clip i+1."""
     mine = shard_clips(num_clips, rank, world)
     if local.shape[0] != len(mine):
         raise ValueError(f"rank {rank} holds {local.shape[0]} clips, expected {len(mine)}")
-    if world == 1:
-        return local
-    per = (num_clips + world - 1) // world
     tail = local.shape[1:]
-    send = local.new_zeros((per,) + tuple(tail))
-    send[:len(mine)] = local
+    if world == 1:
+        return _PendingGather(None, local, local, num_clips, 1, num_clips, tail) if async_op else local
+    per = (num_clips + world - 1) // world
+    if len(mine) == per:
+        send = local.contiguous()
+    else:
+        send = local.new_zeros((per,) + tuple(tail))
+        send[:len(mine)] = local
     recv = local.new_empty((world * per,) + tuple(tail))
-    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-    out = local.new_empty((num_clips,) + tuple(tail))
-    recv = recv.view((world, per) + tuple(tail))
-    for r in range(world):
-        ids = shard_clips(num_clips, r, world)
-        if ids:
-            out[ids] = recv[r, :len(ids)]
-    return out
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=async_op)
+    pending = _PendingGather(work if async_op else None, recv, send, num_clips, world, per, tail)
+    return pending if async_op else pending.result()
 
 
 # --------------------------------------------------------------------------------------------------

@@ -72,6 +72,8 @@ def _gather_worker(rank, world, port, num_clips, ret):
         ids = sharding.shard_clips(num_clips, rank, world)
         local = torch.stack([torch.full((3, 4, 5), float(i)) for i in ids]) if ids else torch.empty(0, 3, 4, 5)
         out = sharding.gather_outputs(local, num_clips, rank, world)
+        pending = sharding.gather_outputs(local, num_clips, rank, world, async_op=True)   # overlappable form: same result
+        assert torch.equal(pending.result(), out)
         ret[rank] = out[:, 0, 0, 0].tolist()
     finally:
         dist.destroy_process_group()
