@@ -61,10 +61,12 @@ typedef struct SpeiShape {
   float eps;         /* candidate window of the bf16 pass in normalised relevance units.
                         <= 0 (default): CERTIFIED window.  The staging pass measures the bf16 rounding residual of every query
                         and key patch; by Cauchy-Schwarz |bf16 score - exact score| <= Delta_i for every key of query i
-                        (Delta_i = 1.01 (d_i + (1 + d_i) max_j d_j) + 1.6e-4, typically 3e-3 - 4e-3).  The tensor-core pass
-                        keeps every key within 2 Delta_i of the best bf16 score, the rescoring keeps every key whose bf16
-                        score is >= E - Delta_i (E = exact relevance of the best bf16 candidate): the true argmax cannot be
-                        outside that set.  Queries whose candidate list cannot hold the set take a second tensor-core pass.
+                        (Delta_i = 1.01 (d_i + (1 + d_i) max_j d_j) + 1.6e-4, typically 3e-3 - 4e-3).  The exact rescoring
+                        keeps every key whose bf16 score is >= E - Delta_i (E = exact relevance of the best bf16 candidate):
+                        the true argmax cannot be outside that set.  The tensor-core pass keeps every key within
+                        Delta_i + 1e-3 of the best bf16 score; a query whose set is not covered by what was kept (its
+                        candidate list overflowed, or E is more than 1e-3 below the best bf16 score) takes a second
+                        tensor-core pass that enumerates the set completely.
                         > 0: fixed window eps (round-1 behaviour with 2e-3; cheaper, exact only while no bf16 score is
                         further than eps/2 from its exact value -- NOT certified). */
 } SpeiShape;

@@ -283,8 +283,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         qlin = (qu >= 1 && qu <= kSTileU && u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
         winq = 0.f;
         if (qlin >= 0) {
-          // fixed window (eps > 0) or the certified one: every key within 2 * Delta of the best bf16 score stays a candidate
-          const float wn = p.win > 0.f ? p.win : 2.04f * certified_delta(__ldg(p.dq + qlin), __int_as_float(__ldg(p.dkmax + ix.item)));
+          // fixed window (eps > 0) or the certified one (spei_common.cuh: certified_window)
+          const float wn = p.win > 0.f ? p.win
+                                       : 1.02f * certified_window(certified_delta(__ldg(p.dq + qlin), __int_as_float(__ldg(p.dkmax + ix.item))));
           winq = wn / __ldg(p.rq + qlin);
         }
         floor0 = -INFINITY;

@@ -124,8 +124,9 @@ rescore_kernel(const RescoreParams p) {
   float max_err = fabsf(bn - E);
   int nres = 1, nviol = (p.eps <= 0.f && max_err > delta) ? 1 : 0;
 
-  // saturation: the last (smallest) entry of some list is still at or above the threshold
-  bool sat = false;
+  // saturation: the last (smallest) entry of some list is still at or above the threshold -- or, certified mode, the
+  // threshold lies below what the tensor-core pass kept (best bf16 score off by more than kWindowMargin)
+  bool sat = p.eps <= 0.f && thr < bn - certified_window(delta);
   for (int sg = lane; sg < nlists; sg += 32) {
     const int e = sg * kTopK + (kTopK - 1);
     if (__ldg(ci + e) >= 0 && __ldg(cv + e) * rq >= thr) sat = true;

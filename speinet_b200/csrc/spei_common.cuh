@@ -97,6 +97,13 @@ int launch_relevance_flagged(const Plan& p, int32_t* stats, char* ws, cudaStream
 __host__ __device__ inline float certified_delta(float dq, float dkmax) {
   return 1.01f * (dq + (1.f + dq) * dkmax) + kAccSlack;
 }
+// Window of the tcgen05 pass in certified mode: Delta + kWindowMargin below a list's best bf16 score.  The rescoring needs
+// every key with bf16 score >= E - Delta (E = exact relevance of the best bf16 candidate b); the lists hold all keys above
+// b - (Delta + margin), which covers that set whenever E >= b - margin.  A query whose best candidate's bf16 score is off by
+// more than the margin (rigorously possible up to Delta, measured <= 6e-4) is queued for the second pass like a saturated one,
+// so the result stays certified while the common case pays for a 1.6x narrower window than the worst-case 2 * Delta.
+constexpr float kWindowMargin = 1.0e-3f;
+__host__ __device__ inline float certified_window(float delta) { return delta + kWindowMargin; }
 int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st);
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
                        const int32_t* arg32, const float* ref, float* out, cudaStream_t st);
