@@ -6,7 +6,7 @@
  *   model/SearchTransfer.py:59-72   SelfTransfer search half -> spei_search_transfer with NULL pyramids
  *   model/speinet.py:93-94,96-97,108-109  _decode fusion     -> spei_fuse_level
  *   model/rcl.py:22-51              r_l_per_channel          -> spei_rl_deconv
- *   relu(conv1x1(bicubic_x2(x))) chains (SearchTransfer.py:70-76, speinet.py:99-100,111-112) -> spei_upsample2_bias_act
+ *   relu(conv1x1(bicubic_x2(x))) chains (SearchTransfer.py:70-76, speinet.py:99-100,111-112) -> spei_conv1x1 + spei_upsample2_bias_act
  *
  * Conventions
  *   - extern "C", plain pointers + sizes + a CUDA stream handle (void*, a cudaStream_t).  No torch types.
@@ -155,10 +155,16 @@ int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, c
 int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32_t num_iterations,
                    float regularization_strength, const float *image, const float *blur_kernel, float *out, void *stream);
 
+/* y = W . x, the channel mix of a 1x1 convolution WITHOUT its bias (fp32 FMA): the first half of the
+ * `relu(conv1x1(F.interpolate(x, scale_factor=2, mode='bicubic')))` chains, applied at low resolution (see below).
+ *   x [n, cin, pixels] fp32, weight [cout, cin] fp32 (Conv2d 1x1 weight), y [n, cout, pixels] fp32; cout in {8,16,32,64,128} */
+int spei_conv1x1(int32_t n, int32_t cin, int32_t cout, int64_t pixels, const float *x, const float *weight, float *y,
+                 void *stream);
+
 /* out = act(bicubic_x2(y) + bias): the second half of the `relu(conv1x1(F.interpolate(x, scale_factor=2, mode='bicubic')))`
  * chains of SelfTransfer (model/SearchTransfer.py:70-76) and _decode (model/speinet.py:99-100, 111-112).  A 1x1 convolution
- * and a per-channel resize commute, so the caller applies the channel mix W . x at LOW resolution (any GEMM) and passes the
- * result as y:
+ * and a per-channel resize commute, so the caller applies the channel mix W . x at LOW resolution (spei_conv1x1) and passes
+ * the result as y:
  *   y    [n, c, h, w] fp32      W . x (no bias)
  *   bias [c] fp32 or NULL       the convolution's bias, added after the resize
  *   relu 0 / 1                  activation

@@ -46,6 +46,7 @@ SIGNATURES = {
     "spei_gather_fold": (ctypes.c_int, [_SH, ctypes.c_int, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "spei_fuse_level": (ctypes.c_int, [ctypes.c_int32] * 5 + [_P] * 7),
     "spei_rl_deconv": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_float] + [_P] * 4),
+    "spei_conv1x1": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.c_int64, _P, _P, _P, _P]),
     "spei_upsample2_bias_act": (ctypes.c_int, [ctypes.c_int32] * 4 + [_P, _P, ctypes.c_int32, _P, _P]),
     "spei_debug_relevance_tile": (ctypes.c_int, [_SH, _P, _P, ctypes.c_size_t, _P]),
     "spei_debug_error_flag": (ctypes.c_int, [_SH, _P, ctypes.c_size_t, _P, ctypes.POINTER(ctypes.c_int32)]),

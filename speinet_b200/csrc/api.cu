@@ -357,6 +357,16 @@ int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32
   return launch_rl_deconv(n, c, h, w, ks, num_iterations, regularization_strength, image, blur_kernel, out, (cudaStream_t)stream);
 }
 
+int spei_conv1x1(int32_t n, int32_t cin, int32_t cout, int64_t pixels, const float* x, const float* weight, float* y, void* stream) {
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  if (n < 1 || cin < 1 || cout < 1 || pixels < 1) { set_error("bad conv1x1 dims n=%d cin=%d cout=%d pixels=%lld", n, cin, cout, (long long)pixels); return SPEI_ERR_ARG; }
+  if ((rc = check_ptr(x, "x", 4)) || (rc = check_ptr(weight, "weight", 4)) || (rc = check_ptr(y, "y", 4))) return rc;
+  if ((const void*)y == (const void*)x) { set_error("conv1x1: y must not alias x"); return SPEI_ERR_ARG; }
+  return launch_conv1x1(n, cin, cout, pixels, x, weight, y, (cudaStream_t)stream);
+}
+
 int spei_upsample2_bias_act(int32_t n, int32_t c, int32_t h, int32_t w, const float* y, const float* bias, int32_t relu, float* out,
                             void* stream) {
   int sms = 0;

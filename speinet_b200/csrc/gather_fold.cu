@@ -11,8 +11,6 @@
 // The <=9 terms are added in the order of torch's col2im so the result is bit-identical to
 // F.fold: ascending patch origin on CUDA (ATen/native/cuda/im2col.cuh:139-154), ascending (ki,kj)
 // on CPU (ATen/native/im2col.h:131-146); then x*(1/9f) resp. x/9 (hard part 4).
-#include <cstdlib>
-
 #include "spei_common.cuh"
 
 namespace spei {
@@ -41,12 +39,12 @@ __device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0
 
 __device__ const float4 g_zero16 = {0.f, 0.f, 0.f, 0.f};  // source of every non-contributing neighbour
 
-// Channel-slab variant for the finest level (S = 4, 118 MB of reference per 720p item): with a scattered match
-// field every reference pixel is covered by ~9 different gathered patches at unrelated times, and the whole level
-// does not stay in L2, so the kernel above re-reads it ~9x from DRAM (ncu: 1.19 GB per launch).  Here the
-// slowest grid dimension is an 8-channel slab (29.5 MB at 720p, L2 resident while every query cell is processed
-// for it), so DRAM sees each slab once; one block handles the S sub-rows of a cell row so the index decode is
-// still shared by S x 8 x 32 outputs.  Same adds in the same order: bit-identical to the kernel above.
+// Finest level (S = 4, 118 MB of reference per 720p item), gathered straight from the planar NCHW input (its 16-byte runs
+// are already whole cell rows).  With a scattered match field every reference pixel is covered by ~9 different gathered
+// patches at unrelated times, and the whole level does not stay in L2: a cell-major order re-read it ~9x from DRAM (ncu,
+// round 1: 1.19 GB per launch).  Here the slowest grid dimension is an 8-channel slab (29.5 MB at 720p, L2 resident while
+// every query cell is processed for it), so DRAM sees each slab once; one block handles the S sub-rows of a cell row so the
+// index decode is shared by S x 8 x 32 outputs.
 // grid: (ceil(W/32), H, n * C/8)   block: (32 cells, 8 channels)
 template <int S, bool kCpuOrder, bool kTrueDiv>
 __global__ void __launch_bounds__(256)
@@ -103,96 +101,17 @@ gather_fold_slab_kernel(const int32_t* __restrict__ arg, const float* __restrict
   }
 }
 
-// grid: (ceil(W/32), S*H, n)   block: (32 cells, 8 channel lanes)
-template <int S, bool kCpuOrder, bool kTrueDiv>
-__global__ void __launch_bounds__(256)
-gather_fold_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
-                   int H, int W, int Hr, int Wr) {
-  using V = typename Vec<S>::T;
-  __shared__ long long s_off[9][32];  // per (neighbour, cell): float offset of the source run, -1 = no contribution
-  const int X0 = blockIdx.x * 32, X = X0 + threadIdx.x;
-  const int y = blockIdx.y, n = blockIdx.z;
-  const int Y = y / S;
-  const int lk1 = Hr * Wr, jmax = rf * lk1 - 1;
-  const size_t ref_plane = (size_t)(S * Hr) * (S * Wr);  // one channel of one reference frame
-  const int ref_pitch = S * Wr;
-
-  // decode the <=9 neighbours of the block's 32 cells ONCE, cooperatively (288 decodes over 256 threads);
-  // the integer divisions of the index decode would otherwise dominate the instruction count of every thread
-  const int32_t* a = arg + (size_t)n * H * W;
-  for (int e = threadIdx.y * 32 + threadIdx.x; e < 9 * 32; e += 256) {
-    const int t = e >> 5, cell = e & 31;
-    // CUDA col2im order: ascending (h_col, w_col); CPU order: ascending (ki,kj) = descending origin
-    const int tt = kCpuOrder ? 8 - t : t;
-    const int dy = tt / 3 - 1, dx = tt % 3 - 1;
-    const int Xc = X0 + cell, qy = Y + dy, qx = Xc + dx;
-    long long o = -1;
-    if (Xc < W && qy >= 0 && qy < H && qx >= 0 && qx < W) {
-      int j = __ldg(a + qy * W + qx);
-      j = min(max(j, 0), jmax);
-      const int f = j / lk1, rem = j - f * lk1;
-      const int hr = rem / Wr, wr = rem - hr * Wr;
-      const int cy = Y + hr - qy, cx = Xc + wr - qx;  // source cell
-      if (cy >= 0 && cy < Hr && cx >= 0 && cx < Wr)
-        o = (long long)f * C * (long long)ref_plane + (long long)(cy * S + (y - Y * S)) * ref_pitch + (long long)cx * S;
-    }
-    s_off[t][cell] = o;
-  }
-  __syncthreads();
-  if (X >= W) return;
-  // Branch-free inner loop: a neighbour without a contribution reads a 16-byte zero constant with channel
-  // stride 0 (adding +0.0f never changes an fp32 sum that started at +0.0f), so the 9 loads and 9 adds per
-  // channel carry no predicates and the per-channel address is one multiply-add.
-  const float* rbase = ref + (size_t)n * rf * C * ref_plane;
-  const float* base[9];
-  unsigned step[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const long long o = s_off[t][threadIdx.x];
-    base[t] = o >= 0 ? rbase + o : reinterpret_cast<const float*>(&g_zero16);
-    step[t] = o >= 0 ? (unsigned)ref_plane : 0u;
-  }
-  const size_t out_plane = (size_t)(S * H) * (S * W);
-  float* obase = out + (size_t)n * C * out_plane + (size_t)y * (S * W) + (size_t)X * S;
-  const int cpt = C / 8;
-#pragma unroll 2
-  for (int ci = 0; ci < cpt; ++ci) {
-    const unsigned c = threadIdx.y * cpt + ci;
-    V v[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = __ldg(reinterpret_cast<const V*>(base[t] + (size_t)c * step[t]));
-    V acc = vzero(V{});
-#pragma unroll
-    for (int t = 0; t < 9; ++t) vadd(acc, v[t]);
-    // streaming (evict-first) store: the output is written once, the gathered reference should keep the L2
-    __stcs(reinterpret_cast<V*>(obase + (size_t)c * out_plane), fin<kTrueDiv>(acc));
-  }
-}
-
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
                        const float* ref, float* out, cudaStream_t st) {
-  dim3 grid((w + 31) / 32, scale * h, n), block(32, 8);
   if (c % 8) { set_error("gather_fold: channels must be a multiple of 8"); return SPEI_ERR_ARG; }
-#define GF(S_, O_, D_) gather_fold_kernel<S_, O_, D_><<<grid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
-#define GFS(S_)                                             \
-  do {                                                      \
-    if (cpu_order) { if (true_div) GF(S_, true, true); else GF(S_, true, false); }  \
-    else { if (true_div) GF(S_, false, true); else GF(S_, false, false); }          \
-  } while (0)
+  if (scale != 4) { set_error("gather_fold (planar source): only the finest level (scale 4) takes this kernel"); return SPEI_ERR_ARG; }
+  if ((long long)n * (c / 8) > 65535 || h > 65535) { set_error("gather_fold: grid too large (n * c / 8 = %lld)", (long long)n * (c / 8)); return SPEI_ERR_ARG; }
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
-  static const bool no_slab = getenv("SPEI_GATHER_NO_SLAB") != nullptr;  // A/B switch
-  if (scale == 4 && !no_slab && (long long)n * (c / 8) <= 65535) {
-    const dim3 sgrid((w + 31) / 32, h, n * (c / 8));
+  const dim3 sgrid((w + 31) / 32, h, n * (c / 8)), block(32, 8);
 #define GFL(O_, D_) gather_fold_slab_kernel<4, O_, D_><<<sgrid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
-    if (cpu_order) { if (true_div) GFL(true, true); else GFL(true, false); }
-    else { if (true_div) GFL(false, true); else GFL(false, false); }
+  if (cpu_order) { if (true_div) GFL(true, true); else GFL(true, false); }
+  else { if (true_div) GFL(false, true); else GFL(false, false); }
 #undef GFL
-  }
-  else if (scale == 1) GFS(1);
-  else if (scale == 2) GFS(2);
-  else GFS(4);
-#undef GFS
-#undef GF
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }

@@ -149,7 +149,6 @@ int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, 
   if (n > 65535 || h > 65535) { set_error("gather_fold: grid too large"); return SPEI_ERR_ARG; }
   if (scale == 1 && c == 128) return launch_gf_nhwc_t<1, 128>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, out, st);
   if (scale == 2 && c == 64) return launch_gf_nhwc_t<2, 64>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, out, st);
-  if (scale == 4 && c == 32) return launch_gf_nhwc_t<4, 32>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, out, st);
   set_error("gather_fold (channels-last): unsupported scale/channels %d/%d", scale, c);
   return SPEI_ERR_ARG;
 }

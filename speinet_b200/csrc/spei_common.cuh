@@ -120,6 +120,7 @@ constexpr int kCntWords = 8;
 int launch_rl_deconv(int n, int c, int h, int w, int ks, int iters, float lambda, const float* img, const float* kern, float* out,
                      cudaStream_t st);
 
+int launch_conv1x1(int n, int cin, int cout, long long P, const float* x, const float* w, float* y, cudaStream_t st);
 int launch_upsample2_bias_act(int n, int c, int h, int w, const float* y, const float* bias, int relu, float* out, cudaStream_t st);
 
 // position <-> index helpers shared by kernels

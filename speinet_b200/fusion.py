@@ -52,8 +52,8 @@ def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torc
 
 def up2_conv1x1_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, relu: bool = True) -> torch.Tensor:
     """act(conv1x1(F.interpolate(x, scale_factor=2, mode='bicubic'); weight, bias)) without materialising the resized
-    input: the 1x1 convolution and the per-channel resize commute, so the channel mix runs at LOW resolution (one
-    library GEMM on a quarter of the pixels, fp32) and `spei_upsample2_bias_act` does resize + bias + ReLU in one pass.
+    input: the 1x1 convolution and the per-channel resize commute, so the channel mix runs at LOW resolution
+    (`spei_conv1x1`, fp32 FMA on a quarter of the pixels) and `spei_upsample2_bias_act` does resize + bias + ReLU in one pass.
     Call sites in the reference: SearchTransfer.py:70-76 (SelfTransfer), speinet.py:99-100 and 111-112 (_decode)."""
     lib = _lib.load()
     out_dtype = x.dtype
@@ -64,11 +64,13 @@ def up2_conv1x1_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = 
     if wf.shape[1] != cin:
         raise RuntimeError(f"up2_conv1x1_act: weight {tuple(weight.shape)} does not match {cin} input channels (1x1 kernels only)")
     cout = wf.shape[0]
-    y = torch.matmul(wf, xf.view(n, cin, h * w)).view(n, cout, h, w).contiguous()     # W . x at low resolution
+    wf = wf.contiguous()
     bf = bias.detach().float().contiguous() if bias is not None else None
     with torch.cuda.device(xf.device):
+        y = torch.empty((n, cout, h, w), dtype=torch.float32, device=xf.device)       # W . x at low resolution
         out = torch.empty((n, cout, 2 * h, 2 * w), dtype=torch.float32, device=xf.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(xf.device).cuda_stream)
+        _lib.check(lib.spei_conv1x1(n, cin, cout, h * w, _ptr(xf), _ptr(wf), _ptr(y), stream), "spei_conv1x1")
         rc = lib.spei_upsample2_bias_act(n, cout, h, w, _ptr(y), _ptr(bf), 1 if relu else 0, _ptr(out), stream)
         _lib.check(rc, "spei_upsample2_bias_act")
     return out if out_dtype == torch.float32 else out.to(out_dtype)

@@ -89,6 +89,14 @@ class _WorkspaceCache:
         slot["event"], slot["stream"] = ev, stream.cuda_stream
 
 
+    def touch(self, dev: torch.device, stream: torch.cuda.Stream):
+        """A CUDA-graph replay used this device's buffers on `stream`: later eager calls on other streams must wait for it."""
+        with self._lock:
+            slots = [v for k, v in self._slots.items() if k[0] == dev.index]
+        for slot in slots:
+            self.release(slot, stream)
+
+
 _WS = _WorkspaceCache()
 
 
@@ -155,9 +163,16 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
 
 
 class SearchTransfer(nn.Module):
-    """Same surface as the reference class (SearchTransfer.py:7-51)."""
+    """Same surface as the reference class (SearchTransfer.py:7-51).
 
-    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tcs", eps: float = 0.0):
+    `cuda_graph=True` (opt-in): the ~20 kernel launches of a call are captured into a CUDA graph the second time the module
+    sees the same input addresses / shapes (the steady state of an inference loop over same-sized frames, where the caching
+    allocator hands back the same blocks) and replayed afterwards: the host cost of a call drops from ~20 launches +
+    tensor-map encodings to one graph launch (at 256x256 the module is launch-bound).  Graph calls return STATIC output
+    tensors: the next graph call with the same inputs overwrites them, as with any CUDA graph.  Call `reset_graphs()` after
+    `torch.cuda.empty_cache()` (captured addresses may no longer be mapped)."""
+
+    def __init__(self, n_feat: int = 32, fold_mode: str = "cuda", search: str = "tcs", eps: float = 0.0, cuda_graph: bool = False):
         super().__init__()
         # never used in forward, exactly as in the reference (:10-11); kept for strict checkpoint loading
         self.search1 = nn.Conv2d(n_feat * 4, n_feat * 2, kernel_size=1, stride=1, padding=0)
@@ -165,6 +180,8 @@ class SearchTransfer(nn.Module):
         self.fold_mode, self.search, self.eps = fold_mode, search, eps
         self.last_index = None   # R_lv3_star_arg of the last call, int64 [N, H*W]
         self.last_stats = None   # int32 [8] device counters (see include/speinet_b200.h)
+        self.cuda_graph = cuda_graph
+        self._graphs = {}        # input signature -> {"out": persistent buffers, "graph": CUDAGraph or None, "result": tuple}
 
     def bis(self, input, dim, index):
         """Batch index select, kept for API compatibility (SearchTransfer.py:12-22):
@@ -175,9 +192,42 @@ class SearchTransfer(nn.Module):
         target[dim] = index.size(1)
         return torch.gather(input, dim, index.view(shape).expand(target))
 
+    def reset_graphs(self):
+        self._graphs.clear()
+
+    def _call(self, args, out=None):
+        return search_transfer(*args, fold_mode=self.fold_mode, search=self.search, eps=self.eps, out=out)
+
+    def _graphed(self, args):
+        flat = []
+        for a in args:
+            flat.extend(a if isinstance(a, (list, tuple)) else [a])
+        key = tuple((t.data_ptr(), tuple(t.shape), t.dtype, t.device.index) if t is not None else None for t in flat) + \
+            (tuple(id(a) == id(args[1]) for a in args), self.fold_mode, self.search, self.eps)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            res = self._call(args)                      # first sighting: eager (allocations, driver entry points, attribute calls)
+            names = ("S", "T3", "T2", "T1", "arg", "stats")
+            fp32_io = args[0].dtype == torch.float32
+            self._graphs[key] = {"out": {n: t for n, t in zip(names, res) if t is not None} if fp32_io else {}, "graph": None}
+            return res
+        if entry["graph"] is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                entry["result"] = self._call(args, out=entry["out"])
+            entry["graph"] = g
+        entry["graph"].replay()
+        _WS.touch(args[0].device, torch.cuda.current_stream(args[0].device))
+        return entry["result"]
+
     def forward(self, lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3, return_index: bool = False):
-        S, T3, T2, T1, arg, stats = search_transfer(lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3,
-                                                     fold_mode=self.fold_mode, search=self.search, eps=self.eps)
+        args = (lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3)
+        if self.cuda_graph and lrsr_lv3.is_cuda and not torch.cuda.is_current_stream_capturing():
+            S, T3, T2, T1, arg, stats = self._graphed(args)
+        else:
+            S, T3, T2, T1, arg, stats = self._call(args)
         self.last_index, self.last_stats = arg, stats
         if return_index:
             return S, T3, T2, T1, arg

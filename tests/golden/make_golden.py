@@ -77,14 +77,17 @@ def main():
     q[:, :, 0:3, 0:3] = 0                          # query patch at (1,1) is entirely zero
     run_case(ref_mod, "st_edge", q, lv1, lv2, lv3)
 
-    # 4. SelfTransfer search (SearchTransfer.py:59-72): only S is a function of the search
+    # 4. SelfTransfer (SearchTransfer.py:53-79): S from the search (:59-72), T_lv3 = the input itself, T_lv2 / T_lv1 =
+    #    relu(conv1x1(bicubic_x2(.))) with the module's own search1 / search2 (:70-76)
     torch.manual_seed(7)
     selft = ref_mod.SelfTransfer()
     q = torch.randn(1, 128, 8, 12, generator=gen) * 0.2
     with torch.no_grad():
-        S, _, _, _ = selft(q)
-    np.savez_compressed(os.path.join(HERE, "self_transfer.npz"), q=q.numpy(), S=S.numpy())
-    print("self_transfer", tuple(S.shape))
+        S, T3, T2, T1 = selft(q)
+    assert T3 is q
+    np.savez_compressed(os.path.join(HERE, "self_transfer.npz"), q=q.numpy(), S=S.numpy(), T_lv2=T2.numpy(), T_lv1=T1.numpy(),
+                        **{"sd_" + k: v.numpy() for k, v in selft.state_dict().items()})
+    print("self_transfer", tuple(S.shape), tuple(T2.shape), tuple(T1.shape))
 
     # 5. fusion lines speinet.py:93-94, 96-97, 108-109 with conv_lv3/2/1 of speinet.py:55-57
     torch.manual_seed(11)

@@ -333,13 +333,19 @@ def test_bf16_inputs_within_1e2():
     np.testing.assert_allclose(f(T3), w3, rtol=1e-2, atol=1e-3)
 
 
-def test_self_transfer_search(golden):
+def test_self_transfer_matches_reference_golden(golden):
+    """The other branch of SPEINet.forward (speinet.py:147): S from the search, T_lv3 = the input, T_lv2 / T_lv1 from the
+    module's own search1 / search2 chains -- all four outputs against what the reference SelfTransfer produced."""
     g = golden("self_transfer")
     m = speinet_b200.SelfTransfer().cuda()
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}, strict=True)
+    q = cu(g["q"])
     with torch.no_grad():
-        S, T3, T2, T1 = m(cu(g["q"]))
+        S, T3, T2, T1 = m(q)
     np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=RTOL_S, atol=1e-6)
-    assert T3.shape == g["q"].shape and T2.shape == (1, 64, 16, 24) and T1.shape == (1, 32, 32, 48)
+    assert T3 is q
+    np.testing.assert_allclose(T2.cpu().numpy(), g["T_lv2"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(T1.cpu().numpy(), g["T_lv1"], rtol=1e-4, atol=1e-6)
 
 
 # ------------------------------------------------------------------ (d) fusion ------------------
@@ -592,6 +598,33 @@ def test_runs_on_non_default_stream_and_batch_mask():
         torch.cuda.current_stream().wait_stream(side)
     for a, b in zip(full, sub):
         assert torch.equal(a[mask], b)
+
+
+def test_module_cuda_graph_mode_replays_and_matches_eager():
+    """SearchTransfer(cuda_graph=True): first call eager, second call with the same input tensors captures, later calls
+    replay; results are bit-identical to the eager module, new input VALUES in the same tensors are picked up, and tensors
+    at new addresses fall back to a fresh eager call."""
+    torch.manual_seed(41)
+    h, w = 20, 28
+    q = torch.randn(1, 128, h, w, device="cuda") * 0.2
+    lv3 = torch.randn(1, 128, h, w, device="cuda") * 0.04
+    lv2 = torch.randn(1, 64, 2 * h, 2 * w, device="cuda") * 0.04
+    lv1 = torch.randn(1, 32, 4 * h, 4 * w, device="cuda") * 0.04
+    eager = speinet_b200.SearchTransfer().cuda()
+    graphed = speinet_b200.SearchTransfer(cuda_graph=True).cuda()
+    with torch.no_grad():
+        want = [t.clone() for t in eager(q, lv3, lv1, lv2, lv3)]
+        for call in range(4):
+            got = graphed(q, lv3, lv1, lv2, lv3)
+            assert all(torch.equal(a, b) for a, b in zip(got, want)), f"call {call}"
+        assert len(graphed._graphs) == 1 and next(iter(graphed._graphs.values()))["graph"] is not None
+        q.mul_(-1.0).add_(0.01)                       # same tensor, new content: the replay must see it
+        want2 = [t.clone() for t in eager(q, lv3, lv1, lv2, lv3)]
+        got2 = graphed(q, lv3, lv1, lv2, lv3)
+        assert all(torch.equal(a, b) for a, b in zip(got2, want2))
+        q3 = q.clone()                                # new address: eager path again, then its own graph
+        got3 = graphed(q3, lv3, lv1, lv2, lv3)
+        assert all(torch.equal(a, b) for a, b in zip(got3, want2)) and len(graphed._graphs) == 2
 
 
 # ------------------------------------------------------------------ host pipeline / install ------

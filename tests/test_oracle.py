@@ -85,6 +85,15 @@ def test_self_transfer_S(golden):
     np.testing.assert_allclose(S, g["S"], rtol=1e-4, atol=1e-6)
 
 
+def test_self_transfer_chains_vs_reference_golden(golden):
+    """relu(conv1x1(bicubic_x2(.))) twice with the reference module's own search1 / search2 (SearchTransfer.py:70-76)."""
+    g = golden("self_transfer")
+    t2 = np.maximum(oracle.conv1x1(oracle.bicubic_upsample(g["q"], 2), g["sd_search1.weight"], g["sd_search1.bias"]), 0)
+    t1 = np.maximum(oracle.conv1x1(oracle.bicubic_upsample(t2, 2), g["sd_search2.weight"], g["sd_search2.bias"]), 0)
+    np.testing.assert_allclose(t2, g["T_lv2"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(t1, g["T_lv1"], rtol=1e-4, atol=1e-6)
+
+
 def test_multi_reference_extension_reduces_to_single():
     """Rf=2 with the two key sets concatenated: the winner is the better of the two
     single-frame searches."""

@@ -45,7 +45,28 @@ def raw_metrics(rep):
     return "\n".join(out)
 
 
+def traffic_json(reps, out_path):
+    """profiles/ncu_traffic.json: DRAM bytes per launch of every captured kernel (bench.py reads roofline.traffic from it)."""
+    import json
+    import re
+    out = {}
+    for rep in reps:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        h, u = rows[0], rows[1]
+        ri, wi, ni = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for vals in rows[2:]:
+            name = re.sub(r"^void ", "", vals[ni]).split("(")[0].split("::")[-1].split("<")[0]
+            b = float(vals[ri].replace(",", "")) * scale[u[ri]] + float(vals[wi].replace(",", "")) * scale[u[wi]]
+            out.setdefault(name, {"dram_bytes": b, "source": f"ncu --set full capture {rep.split('/')[-1]} (first captured launch), summarised in profiles/"})
+    json.dump(out, open(out_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--traffic":
+        traffic_json(sys.argv[3:], sys.argv[2])
+        sys.exit(0)
     print("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)")
     print(launch_table(sys.argv[1]))
     for rep in sys.argv[2:]:
