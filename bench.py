@@ -45,7 +45,7 @@ CONFIG = {"workload": WORKLOAD, "query_grid": [H, W], "ref_grid": [H, W], "ref_f
 # kernels of this repo launched per step (one clip): see DESIGN.md section 4
 KERNELS_PER_STEP = {"stage (zero_padding, stage_transpose, patch_norms)": 3, "search (relevance_tcs)": 1,
                     "exactness (clear, rescore, flagged pack / tcgen05 emission / rescoring, exhaustive fallback, unpack)": 7,
-                    "gather_fold lv3/lv2/lv1": 3, "fuse_level lv3/lv2/lv1": 3}
+                    "gather_fold lv3/lv2/lv1 (+ the channels-last copy of ref_lv2)": 4, "fuse_level lv3/lv2/lv1": 3}
 
 
 def peaks():
@@ -359,6 +359,13 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:   # one slice of the host cores per rank: the pinned-buffer leg is host-side copy work
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
     host = make_clip(dev, rank, pinned_host=True)
     torch.manual_seed(0)
     convs = {3: torch.nn.Conv2d(2 * C3, C3, 1), 2: torch.nn.Conv2d(C3, C3 // 2, 1), 1: torch.nn.Conv2d(C3 // 2, C3 // 4, 1)}
@@ -394,11 +401,22 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    peer, peer_err = None, None
+    if world > 1:
+        try:    # the path's own gather over NVLink peer memory (copy engines, no SM time); NCCL is the comparison
+            peer = speinet_b200.PeerGather((3, 4 * H, 4 * W), world, rank, world, device=dev)
+        except Exception as e:  # noqa: BLE001
+            peer_err = repr(e)[:200]
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            peer = None
+
     def timed_steps(count, collective):
-        """K steps bracketed by barrier + synchronize.  Every step ends with this clip's frame ([3,720,1280], the stand-in head
-        conv runs at every N so the step is the same work at N = 1) handed to the package's own gather_outputs (NCCL
-        all-gather, asynchronous: NCCL's stream waits for the clip, the compute stream does not wait for NCCL, so the
-        gather of clip i overlaps the search of clip i+1); every handle is completed before the region closes."""
+        """K steps bracketed by barrier + synchronize.  Every step ends with this clip's frame ([3,720,1280]; the stand-in head
+        conv runs at every N so the step is the same work at N = 1) handed to the job's gather -- `collective` = "peer":
+        speinet_b200.PeerGather (NVLink peer memory, copy engines), "nccl": speinet_b200.gather_outputs (all-gather), both
+        asynchronous: the exchange of clip i overlaps the search of clip i+1; every handle is completed before the region closes."""
         tc_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -407,29 +425,35 @@ def run_ours(args, rank, world, local_rank):
         for i in range(count):
             step(events=tc_ev[i])
             frame = frame_of(P)
-            if collective and world > 1:
+            if world > 1 and collective == "nccl":
                 if pending is not None:
                     gathered = pending.result()
                 pending = speinet_b200.gather_outputs(frame, world, rank, world, async_op=True)
+            elif world > 1 and collective == "peer":
+                if pending is not None:
+                    gathered = peer.result(pending, copy=False)
+                pending = peer.push(frame)
         if pending is not None:
-            gathered = pending.result()
+            gathered = peer.result(pending) if collective == "peer" else pending.result()
         e1.record()
         barrier()
         return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in tc_ev], gathered
 
     W_ = max(3, args.warmup)
-    for _ in range(W_):
-        step()
-        speinet_b200.gather_outputs(frame_of(P), world, rank, world)
+    main_mode = "peer" if peer is not None else "nccl"
+    timed_steps(W_, main_mode)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total, tc_ms, gathered = timed_steps(args.steps, collective=True)
+    ms_total, tc_ms, gathered = timed_steps(args.steps, main_mode)
     clocks = sampler.stop()
     cycles = P.search_cycles(stream)
-    ms_nocoll = None
+    ms_nocoll = ms_nccl = None
     if world > 1:
-        ms_nocoll, _, _ = timed_steps(args.steps, collective=False)
+        ms_nocoll, _, _ = timed_steps(args.steps, "none")
+        timed_steps(2, "nccl")
+        ms_nccl, _, g2 = timed_steps(args.steps, "nccl")
+        gather_equal = bool(torch.equal(g2, gathered))
 
     # ---- HBM-bound stages timed alone (events on the launch stream, 10 launches each after 2 warm-ups):
     # achieved = algorithmic bytes / launch time, against the measured copy bandwidth ----
@@ -495,6 +519,28 @@ def run_ours(args, rank, world, local_rank):
     from speinet_b200.pipeline import HostPipeline
     conv_wb = {l: (convs[l].weight.detach(), convs[l].bias.detach()) for l in convs}
     e2e = e2e_bf16 = None
+
+    def host_link_probe():
+        """Raw pinned-memory copy rate of this rank with ALL ranks copying at once (one clip's H2D on one stream, its D2H on
+        another, 6 rounds): the ceiling of the host-buffer leg, whatever the kernels do."""
+        hin = torch.empty(412876800 // 4).pin_memory()
+        hout = torch.empty(206668800 // 4).pin_memory()
+        din, dout = torch.empty_like(hin, device=dev), torch.empty_like(hout, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(6):
+            with torch.cuda.stream(s1):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        gbs = 6 * (hin.numel() + hout.numel()) * 4 / float(dt[0]) / 1e9
+        return {"GBs_per_rank_all_ranks_copying": gbs, "GBs_aggregate": gbs * world,
+                "frames_per_s_ceiling": world * 6 / float(dt[0]), "bytes_per_clip": (hin.numel() + hout.numel()) * 4}
     if not args.no_e2e:
         def e2e_leg(dtype):
             pipe = HostPipeline(conv_wb, dev, cuda_graph=not args.no_graph)
@@ -532,6 +578,7 @@ def run_ours(args, rank, world, local_rank):
                     }, outs[(n_e2e - 1) & 1]
         e2e, out32 = e2e_leg(torch.float32)
         e2e["max_abs_diff_vs_device_path"] = float((out32["f1"] - P.Fo[1].cpu()).abs().max())
+        e2e["host_link_probe"] = host_link_probe()
         if world == 1:
             e2e_bf16, out16 = e2e_leg(torch.bfloat16)
             ref32 = out32["f1"].float()
@@ -542,13 +589,13 @@ def run_ours(args, rank, world, local_rank):
     # ---- N > 1: BASELINE.json configs[4] literally, and the row-band sharding of one large frame ----
     sweep = row_band = None
     if world > 1 and not args.no_sweep:
-        sweep = sweep64(dev, rank, world, P, conv_wb, head, barrier)
+        sweep = sweep64(dev, rank, world, P, conv_wb, head, barrier, peer)
         row_band = row_band_leg(dev, rank, world, barrier)
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_nocoll], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_nocoll, ms_nccl], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_nocoll = float(t[0]), float(t[1])
+        ms_total, ms_nocoll, ms_nccl = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
     peak_burst, peak_sus, hbm, which = peaks()
@@ -567,8 +614,9 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "bf16 tensor-core candidates + f32 rescoring/fold/fusion", "data": "synthetic",
         "config": CONFIG,
         "run_config": {"schedule": "one stream", "candidate_window": "certified (data-dependent bound)" if args.eps <= 0 else args.eps,
-                       "parallelism": (f"clips sharded over {world} ranks, no data-path collective; per step one all-gather of the ranks' "
-                                       "[3,720,1280] frames through speinet_b200.gather_outputs (NCCL)") if world > 1 else "single GPU"},
+                       "parallelism": (f"clips sharded over {world} ranks, no data-path collective; per step the ranks' [3,720,1280] frames "
+                                       "are gathered on every rank (speinet_b200.PeerGather over NVLink peer memory, or gather_outputs / NCCL)")
+                       if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": exec_ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": exec_ach / peak_burst,
                      "frac_of_sustained": exec_ach / peak_sus, "peak_source": which,
@@ -593,7 +641,11 @@ def run_ours(args, rank, world, local_rank):
                                 "stages": secondary},
     }
     if world > 1:
-        line["collective_ab"] = {"ms_per_step_with_gather": ms_total / args.steps, "ms_per_step_without": ms_nocoll / args.steps,
+        line["collective_ab"] = {"value_uses": "speinet_b200.PeerGather (NVLink peer memory, copy engines)" if peer is not None
+                                 else "speinet_b200.gather_outputs (NCCL all-gather, async)",
+                                 "ms_per_step_peer_memory_gather": ms_total / args.steps if peer is not None else None,
+                                 "ms_per_step_nccl_all_gather": ms_nccl / args.steps, "ms_per_step_without_gather": ms_nocoll / args.steps,
+                                 "peer_and_nccl_results_equal": gather_equal, "peer_memory_error": peer_err,
                                  "gathered_shape": list(gathered.shape) if gathered is not None else None}
         line["sweep64"], line["row_band"] = sweep, row_band
     if world == 1 and not args.no_cpu_baseline:
@@ -615,9 +667,10 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def sweep64(dev, rank, world, P, conv_wb, head, barrier, clips=64):
+def sweep64(dev, rank, world, P, conv_wb, head, barrier, peer, clips=64):
     """BASELINE.json configs[4]: 64 synthetic 720p clips, `clip_id % world` -> rank (speinet_b200.shard_clips), every clip through the
-    public modules, the per-clip [3,720,1280] frames gathered with speinet_b200.gather_outputs over NCCL; rank 0 then recomputes four
+    public modules, the per-clip [3,720,1280] frames gathered on every rank (speinet_b200.PeerGather; NCCL gather_outputs if peer
+    memory is unavailable); rank 0 then recomputes four
     clips owned by OTHER ranks and checks the gathered frames bit for bit (= the single-GPU result: the kernels are deterministic).
     Strong scaling: total work fixed."""
     import speinet_b200
@@ -633,12 +686,28 @@ def sweep64(dev, rank, world, P, conv_wb, head, barrier, clips=64):
     with torch.no_grad():
         data = [make_clip(dev, cid) for cid in mine]
         clip_frame(data[0])
+        pg = peer if (peer is not None and clips % world == 0) else None
+        full = torch.empty(clips, 3, 4 * H, 4 * W, device=dev) if pg is not None else None
         barrier()
         t0 = time.perf_counter()
-        local = torch.cat([clip_frame(c) for c in data], dim=0)
-        torch.cuda.synchronize(dev)
-        t_compute = time.perf_counter() - t0
-        full = speinet_b200.gather_outputs(local, clips, rank, world)
+        if pg is not None:
+            # one exchange per round of `world` clips, overlapped with the next clip's kernels; exchange i carries clips
+            # i * world .. i * world + world - 1 in rank order = clip order (shard_clips is round-robin)
+            pending, done = None, 0
+            for c in data:
+                frame = clip_frame(c)
+                if pending is not None:
+                    pg.result(pending, out=full[done:done + world])
+                    done += world
+                pending = pg.push(frame)
+            pg.result(pending, out=full[done:done + world])
+            torch.cuda.synchronize(dev)
+            t_compute = time.perf_counter() - t0
+        else:
+            local = torch.cat([clip_frame(c) for c in data], dim=0)
+            torch.cuda.synchronize(dev)
+            t_compute = time.perf_counter() - t0
+            full = speinet_b200.gather_outputs(local, clips, rank, world)
         barrier()
         t_all = time.perf_counter() - t0
         del data
@@ -653,7 +722,9 @@ def sweep64(dev, rank, world, P, conv_wb, head, barrier, clips=64):
     return {"clips": clips, "scaling": "strong", "frames_per_s": clips / float(t[1]), "seconds": float(t[1]), "compute_seconds_max_rank": float(t[0]),
             "gathered_shape": list(full.shape), "gathered_bytes": full.numel() * 4,
             "recomputed_on_rank0": check, "gathered_equals_single_gpu_result": equal,
-            "api": "speinet_b200.shard_clips + SearchTransfer + fuse_level + gather_outputs (NCCL all_gather_into_tensor)"}
+            "api": "speinet_b200.shard_clips + SearchTransfer + fuse_level + " +
+                   ("PeerGather (one NVLink peer-memory exchange per round of clips, overlapped)" if pg is not None
+                    else "gather_outputs (NCCL all_gather_into_tensor)")}
 
 
 def row_band_leg(dev, rank, world, barrier):

@@ -67,6 +67,82 @@ def gather_outputs(local: torch.Tensor, num_clips: int, rank: int, world: int, g
     return pending if async_op else pending.result()
 
 
+class PeerGather:
+    """`gather_outputs` over NVLink PEER MEMORY instead of NCCL kernels: every rank copies its shard straight into the peers'
+    symmetric buffers (`torch.distributed._symmetric_memory`; cudaMemcpyPeer = the GPUs' copy engines through NVSwitch) and a
+    device-side signal barrier closes the exchange.  No SM runs collective code, so the power-capped persistent tcgen05 search
+    kernel of the next clip keeps the whole chip -- measured at 8 GPUs the NCCL all-gather of the frames cost 0.5 ms per
+    3.2 ms step even when launched asynchronously (bench.py collective_ab).
+
+    One instance serves a fixed per-clip shape; `slots` exchanges can be in flight.  Usage per step:
+        slot = pg.push(local)          # enqueue (side stream waits for the producer of `local` on the current stream)
+        ...                            # next clip's kernels
+        full = pg.result(slot)         # [num_clips, ...] in clip order; the current stream waits for the exchange"""
+
+    def __init__(self, tail_shape, num_clips: int, rank: int, world: int, dtype=torch.float32, device=None, group=None,
+                 slots: int = 2):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.num_clips, self.slots = rank, world, num_clips, slots
+        self.per = (num_clips + world - 1) // world
+        self.mine = shard_clips(num_clips, rank, world)
+        self.tail = tuple(tail_shape)
+        self.dev = torch.device(device if device is not None else torch.cuda.current_device())
+        shape = (slots, world, self.per) + self.tail
+        self.buf = symm.empty(shape, dtype=dtype, device=self.dev)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peers = [self.hdl.get_buffer(r, shape, dtype) for r in range(world)]
+        self.side = torch.cuda.Stream(self.dev)
+        self.done = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [None] * slots
+        self.pending = [False] * slots
+        self.next_slot = 0
+
+    def push(self, local: torch.Tensor) -> int:
+        if local.shape[0] != len(self.mine) or tuple(local.shape[1:]) != self.tail:
+            raise ValueError(f"rank {self.rank}: expected [{len(self.mine)}, {self.tail}], got {tuple(local.shape)}")
+        slot = self.next_slot
+        self.next_slot = (slot + 1) % self.slots
+        if any(self.pending):
+            # one exchange in flight at a time: result(i) before push(i+1) is what orders this rank's reads of a slot
+            # before the peers' next writes to it (the barrier of exchange i+1 is entered only after those reads)
+            raise RuntimeError("PeerGather: take result() of the previous exchange before the next push()")
+        cur = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            # every earlier result of ANY slot on this rank has been consumed before this rank arrives at the barrier
+            # below; a peer that has passed the barrier may therefore overwrite those slots
+            for ev in self.consumed:
+                if ev is not None:
+                    self.side.wait_event(ev)
+            n = len(self.mine)
+            if n:
+                for r in range(self.world):
+                    self.peers[r][slot, self.rank, :n].copy_(local, non_blocking=True)
+            self.hdl.barrier(channel=slot)
+            self.done[slot].record(self.side)
+        local.record_stream(self.side)
+        self.pending[slot] = True
+        return slot
+
+    def result(self, slot: int, copy: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+        """[num_clips, ...] in clip order (written into `out` when given).  With copy=False (only when every rank holds
+        exactly one clip) a view of the exchange buffer is returned: valid until this rank's next push()."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.done[slot])
+        self.pending[slot] = False
+        recv = self.buf[slot]                                        # [world, per, ...]; clip id = i * world + r
+        if self.per == 1 and self.num_clips == self.world and not copy and out is None:
+            res = recv[:, 0]
+        else:
+            src = recv.transpose(0, 1).reshape((self.world * self.per,) + self.tail)[:self.num_clips] if self.per > 1 \
+                else recv[:self.num_clips, 0]
+            res = src.clone() if out is None else out.copy_(src)
+        ev = self.consumed[slot] or torch.cuda.Event()
+        ev.record(cur)
+        self.consumed[slot] = ev
+        return res
+
+
 # --------------------------------------------------------------------------------------------------
 # Single very large frame: shard the QUERY ROWS of the lv3 grid (second row)
 # --------------------------------------------------------------------------------------------------
