@@ -289,12 +289,13 @@ def parity_vs_reference(ours, ref, q, lv3):
 class DevicePath:
     """The stage sequence of one clip through the C-ABI on caller-owned buffers (what `value` times)."""
 
-    def __init__(self, dev, search, eps=0.0, n=1):
+    def __init__(self, dev, search, eps=0.0, n=1, bf16=False):
         import speinet_b200
         from speinet_b200 import _lib
-        self._lib, self.lib, self.dev = _lib, speinet_b200.load_library(), dev
+        self._lib, self.lib, self.dev, self.bf16 = _lib, speinet_b200.load_library(), dev, bf16
         self.shape = _lib.SpeiShape(n=n, h=H, w=W, hr=H, wr=W, rf=1, c3=C3, c2=C3 // 2, c1=C3 // 4, fold_mode=_lib.FOLD_CUDA,
-                                    search={"tc": _lib.SEARCH_TC, "tcs": _lib.SEARCH_TCS}[search], eps=eps)
+                                    search={"tc": _lib.SEARCH_TC, "tcs": _lib.SEARCH_TCS}[search], eps=eps,
+                                    io_dtype=_lib.IO_BF16 if bf16 else _lib.IO_F32)
         nb = ctypes.c_size_t(0)
         _lib.check(self.lib.spei_workspace_bytes(ctypes.byref(self.shape), ctypes.byref(nb)), "workspace_bytes")
         self.ws_bytes = nb.value
@@ -303,8 +304,9 @@ class DevicePath:
         self.S = torch.empty(n, 1, H, W, device=dev)
         self.arg32 = torch.empty(n, L, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(_lib.STATS_WORDS, dtype=torch.int32, device=dev)
-        self.T = {3: torch.empty(n, C3, H, W, device=dev), 2: torch.empty(n, C3 // 2, 2 * H, 2 * W, device=dev),
-                  1: torch.empty(n, C3 // 4, 4 * H, 4 * W, device=dev)}
+        io = torch.bfloat16 if bf16 else torch.float32
+        self.T = {3: torch.empty(n, C3, H, W, device=dev, dtype=io), 2: torch.empty(n, C3 // 2, 2 * H, 2 * W, device=dev, dtype=io),
+                  1: torch.empty(n, C3 // 4, 4 * H, 4 * W, device=dev, dtype=io)}
         self.Fo = {l: torch.empty_like(self.T[l]) for l in self.T}
         self.sref = ctypes.byref(self.shape)
 
@@ -329,8 +331,9 @@ class DevicePath:
 
     def fuse(self, lvl, dec, wt, st):
         c, sc = self.T[lvl].shape[1], {3: 1, 2: 2, 1: 4}[lvl]
-        self._lib.check(self.lib.spei_fuse_level(self.shape.n, c, H, W, sc, self.vp(dec), self.vp(self.T[lvl]), self.vp(self.S), self.vp(wt[0]),
-                                                 self.vp(wt[1]), self.vp(self.Fo[lvl]), st), "fuse_level")
+        fn = self.lib.spei_fuse_level_bf16 if self.bf16 else self.lib.spei_fuse_level
+        self._lib.check(fn(self.shape.n, c, H, W, sc, self.vp(dec), self.vp(self.T[lvl]), self.vp(self.S), self.vp(wt[0]),
+                           self.vp(wt[1]), self.vp(self.Fo[lvl]), st), "fuse_level")
 
     def search_cycles(self, st):
         out = (ctypes.c_int64 * 2)()
@@ -514,6 +517,46 @@ def run_ours(args, rank, world, local_rank):
     tile_n, taps = (32, 3) if args.search == "tcs" else (8, 9)
     flops_exec = 2.0 * plan["QT"] * plan["KT"] * 128 * (tile_n * plan["k_Ny"]) * taps * C3
 
+    # ---- BASELINE.json configs[2] "fp32-accum vs bf16": the same step with NATIVE bf16 I/O (SPEI_IO_BF16: every feature tensor
+    # bf16 in HBM, fp32 accumulation everywhere), device-resident, with its own HBM rooflines (bf16 algorithmic bytes) ----
+    bf16_leg = None
+    if rank == 0 and not args.no_bf16:
+        Pb = DevicePath(dev, args.search, eps=args.eps, bf16=True)
+        db = {k: v.bfloat16() for k, v in d.items()}
+        kb5 = db["lv3"].unsqueeze(1)
+        refs_b = {3: kb5, 2: db["lv2"].unsqueeze(1), 1: db["lv1"].unsqueeze(1)}
+        decs_b = {3: db["q"], 2: db["dec2"], 1: db["dec1"]}
+
+        def step_b():
+            Pb.stage(db["q"], kb5, stream)
+            Pb.candidates(stream)
+            Pb.rescore(stream)
+            for lvl in (3, 2, 1):
+                Pb.gather(lvl, refs_b[lvl], kb5, stream)
+            for lvl in (3, 2, 1):
+                Pb.fuse(lvl, decs_b[lvl], wts[lvl], stream)
+        t_step = timed_ms(step_b, iters=max(5, args.steps))
+        stages = [{"stage": "a_stage_norm(q+k)", "ms": timed_ms(lambda: Pb.stage(db["q"], kb5, stream)), "bytes": 2 * (2 + 2 + 4) * C3 * L},
+                  {"stage": "b_search(relevance_tcs)", "ms": timed_ms(lambda: Pb.candidates(stream), iters=5), "bytes": None}]
+        for lvl in (3, 2, 1):
+            stages.append({"stage": f"c_gather_fold_lv{lvl}", "ms": timed_ms(lambda: Pb.gather(lvl, refs_b[lvl], kb5, stream)),
+                           "bytes": 2 * Pb.T[lvl].numel() * 2})
+        for lvl in (3, 2, 1):
+            stages.append({"stage": f"d_fuse_lv{lvl}", "ms": timed_ms(lambda: Pb.fuse(lvl, decs_b[lvl], wts[lvl], stream)),
+                           "bytes": 3 * Pb.T[lvl].numel() * 2})
+        for r in stages:
+            if r["bytes"]:
+                r["achieved_GBs"] = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+                r["frac_of_hbm_peak"] = r["achieved_GBs"] / hbm_peak
+        step()
+        torch.cuda.synchronize(dev)
+        ref1 = P.Fo[1]
+        bf16_leg = {"dtype": "bf16 I/O (SPEI_IO_BF16), fp32 accumulation", "ms_per_step": t_step, "frames_per_s": 1e3 / t_step,
+                    "stages": stages, "search_stats": dict(zip(_lib.STATS_NAMES, Pb.stats.cpu().tolist())),
+                    "max_abs_diff_f1_vs_fp32_step": float((Pb.Fo[1].float() - ref1).abs().max()), "max_abs_f1": float(ref1.abs().max()),
+                    "note": "inputs = the fp32 step's inputs rounded to bf16; difference includes that input rounding (north_star bar 1e-2)"}
+        del Pb, db
+
     # ---- end to end through the public API with host buffers (speinet_b200.HostPipeline: H2D, compute and
     # D2H of consecutive clips overlap on three streams; every clip's copies are inside the timed region) ----
     from speinet_b200.pipeline import HostPipeline
@@ -632,7 +675,7 @@ def run_ours(args, rank, world, local_rank):
                                        "achieved": FLOPS_RELEVANCE / (dense["candidates_ms"] * 1e-3) / 1e12,
                                        "frac": FLOPS_RELEVANCE / (dense["candidates_ms"] * 1e-3) / 1e12 / peak_burst} if dense else None),
                      "traffic": traffic, "traffic_source": traffic_src},
-        "e2e": e2e, "e2e_bf16_io": e2e_bf16,
+        "e2e": e2e, "e2e_bf16_io": e2e_bf16, "bf16_io_device_resident": bf16_leg,
         "gpu_launches": sum(KERNELS_PER_STEP.values()) * args.steps, "gpu_launches_per_step": KERNELS_PER_STEP,
         "clocks": clocks,
         "search_stats_last_step": dict(zip(_lib.STATS_NAMES, P.stats.cpu().tolist())), "plan": plan,
@@ -764,6 +807,7 @@ def main():
     ap.add_argument("--eps", type=float, default=0.0, help="candidate window; <= 0 = certified data-dependent window (default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs only; not a valid bench line)")
     ap.add_argument("--no-graph", action="store_true", help="host-buffer leg without CUDA graphs")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the native bf16 I/O leg")
     ap.add_argument("--no-sweep", action="store_true", help="N > 1: skip the 64-clip sweep and the row-band leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

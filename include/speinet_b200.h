@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - extern "C", plain pointers + sizes + a CUDA stream handle (void*, a cudaStream_t).  No torch types.
- *   - every pointer is DEVICE memory owned by the caller; tensors are contiguous NCHW fp32 unless stated.
+ *   - every pointer is DEVICE memory owned by the caller; tensors are contiguous NCHW, fp32 unless SpeiShape.io_dtype /
+ *     the _bf16 entry points say bf16.
  *   - the library never allocates persistent device memory, never frees caller memory and never
  *     synchronises the device; all work is enqueued on `stream`.
  *   - return value 0 = ok, negative = error (SPEI_ERR_*); spei_last_error() returns a thread-local message.
@@ -39,6 +40,12 @@ extern "C" {
 #define SPEI_FOLD_TRUE_DIV 2  /* bit 1: true division by 9 instead of x * (1.0f/9.0f)          */
 #define SPEI_FOLD_CUDA 0      /* what torch does on a CUDA device: CUDA col2im order, x*(1/9f) */
 #define SPEI_FOLD_CPU 3       /* what torch does on the CPU: CPU col2im order, x/9             */
+
+/* element type of the feature tensors that cross the boundary */
+#define SPEI_IO_F32 0
+#define SPEI_IO_BF16 1 /* q, k, ref1/2/3 and T3/T2/T1 are bf16 (north_star's 1e-2 mode): every kernel reads / writes bf16 natively,
+                          arithmetic stays fp32 (search candidates bf16 -- now EXACT operands --, rescoring / fold sums fp32).
+                          S, arg and stats keep their types. */
 
 /* relevance engine */
 #define SPEI_SEARCH_TC 0    /* tcgen05 bf16 candidate pass, dense 9-tap implicit GEMM, + exact fp32 rescoring */
@@ -69,6 +76,7 @@ typedef struct SpeiShape {
                         tensor-core pass that enumerates the set completely.
                         > 0: fixed window eps (round-1 behaviour with 2e-3; cheaper, exact only while no bf16 score is
                         further than eps/2 from its exact value -- NOT certified). */
+  int32_t io_dtype;  /* SPEI_IO_F32 (0) or SPEI_IO_BF16                                          */
 } SpeiShape;
 
 /* Counters written by spei_search_transfer / spei_relevance_argmax / spei_rescore into caller memory (device,
@@ -102,8 +110,8 @@ int spei_workspace_bytes(const SpeiShape *shape, size_t *bytes);
  *   arg    [n, h*w] int64             R_lv3_star_arg, key index j = f*hr*wr + y*wr + x   (:34)  (may be NULL)
  *   stats  SPEI_STATS_WORDS x int32 device counters (may be NULL)
  */
-int spei_search_transfer(const SpeiShape *shape, const float *q, const float *k, const float *ref1,
-                         const float *ref2, const float *ref3, float *S, float *T3, float *T2, float *T1,
+int spei_search_transfer(const SpeiShape *shape, const void *q, const void *k, const void *ref1,
+                         const void *ref2, const void *ref3, float *S, void *T3, void *T2, void *T1,
                          int64_t *arg, int32_t *stats, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- individual stages (the pipeline above is exactly these, in this order) ---- */
@@ -111,7 +119,7 @@ int spei_search_transfer(const SpeiShape *shape, const float *q, const float *k,
 /* (a) unfold + normalize pre-pass (SearchTransfer.py:26-31) without materialising the unfolded
  * tensors: stages q and k into the layouts the search kernels read and computes the per-patch
  * reciprocal L2 norms.  Fills the staging part of `workspace`. */
-int spei_stage_norm(const SpeiShape *shape, const float *q, const float *k, void *workspace,
+int spei_stage_norm(const SpeiShape *shape, const void *q, const void *k, void *workspace,
                     size_t workspace_bytes, void *stream);
 
 /* (b) relevance bmm + max/argmax (SearchTransfer.py:33-34) on the staged operands.
@@ -132,8 +140,8 @@ int spei_rescore(const SpeiShape *shape, float *S, int32_t *arg32, int64_t *arg6
  * lv3 / lv2 gather from a channels-last copy kept in `workspace`; `staged_k` is the refsr_lv3 pointer
  * last given to spei_stage_norm with this workspace (or NULL): when `ref == staged_k` at level 3 the copy
  * made there is reused (ref_lv3 and refsr_lv3 are the same tensor at speinet.py:135). */
-int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, const float *ref, float *out,
-                     const float *staged_k, void *workspace, size_t workspace_bytes, void *stream);
+int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, const void *ref, void *out,
+                     const void *staged_k, void *workspace, size_t workspace_bytes, void *stream);
 
 /* (d) one fusion line of SPEINet._decode (speinet.py:93-94 / 96-97 / 108-109):
  *   out = dec + (W . cat(dec, t) + b) * bicubic_up(S, scale),  scale in {1,2,4}
@@ -141,6 +149,11 @@ int spei_gather_fold(const SpeiShape *shape, int level, const int32_t *arg32, co
  *   bias [c]; S [n, 1, h, w].  out may alias neither input. */
 int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const float *dec, const float *t,
                     const float *S, const float *weight, const float *bias, float *out, void *stream);
+
+/* The same fusion line with bf16 dec / t / out (S, weight, bias stay fp32; fp32 accumulation, one rounding at the store).
+ * TMA-fed kernel only: scale*h * scale*w must be a multiple of 8 and dec / t / out / weight 16-byte aligned. */
+int spei_fuse_level_bf16(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const void *dec, const void *t,
+                         const float *S, const float *weight, const float *bias, void *out, void *stream);
 
 /* ---- next to the path ---- */
 

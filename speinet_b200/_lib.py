@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("SPEINET_B200_LIB") or os.path.join(_PKG, "libspeinet_
 FOLD_CUDA, FOLD_CPU = 0, 3
 FOLD_ORDER_CPU, FOLD_TRUE_DIV = 1, 2
 SEARCH_TC, SEARCH_EXACT, SEARCH_TCS = 0, 1, 2
+IO_F32, IO_BF16 = 0, 1
 STATS_WORDS = 8   # SPEI_STATS_WORDS
 STATS_NAMES = ("saturated_queries", "pairs_rescored", "max_bf16_vs_exact_x1e9", "exhaustive_fallback", "reserved4",
                "second_pass_pairs_emitted", "certified_bound_violations", "reserved7")
@@ -28,6 +29,7 @@ class SpeiShape(ctypes.Structure):
         ("hr", ctypes.c_int32), ("wr", ctypes.c_int32), ("rf", ctypes.c_int32),
         ("c3", ctypes.c_int32), ("c2", ctypes.c_int32), ("c1", ctypes.c_int32),
         ("fold_mode", ctypes.c_int32), ("search", ctypes.c_int32), ("eps", ctypes.c_float),
+        ("io_dtype", ctypes.c_int32),
     ]
 
 
@@ -45,6 +47,7 @@ SIGNATURES = {
     "spei_rescore": (ctypes.c_int, [_SH, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "spei_gather_fold": (ctypes.c_int, [_SH, ctypes.c_int, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "spei_fuse_level": (ctypes.c_int, [ctypes.c_int32] * 5 + [_P] * 7),
+    "spei_fuse_level_bf16": (ctypes.c_int, [ctypes.c_int32] * 5 + [_P] * 7),
     "spei_rl_deconv": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_float] + [_P] * 4),
     "spei_conv1x1": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.c_int64, _P, _P, _P, _P]),
     "spei_upsample2_bias_act": (ctypes.c_int, [ctypes.c_int32] * 4 + [_P, _P, ctypes.c_int32, _P, _P]),

@@ -65,6 +65,7 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.mode = shared ? SPEI_SEARCH_TCS : SPEI_SEARCH_TC;
   p.nlist = shared ? tcs_epilogue_groups() : 1;
   p.n = s.n; p.rf = s.rf; p.H = s.h; p.W = s.w; p.Hr = s.hr; p.Wr = s.wr;
+  p.io_bf16 = s.io_dtype == SPEI_IO_BF16;
   if (!shared) {
     // the MMA applies all nine taps with per-operand address offsets: each operand picks its own orientation
     p.q = plan_operand(s.h, s.w, false, false);
@@ -158,6 +159,7 @@ static int check_shape(const SpeiShape* s) {
     set_error("index space exceeds int32"); return SPEI_ERR_ARG;
   }
   if (s->fold_mode < 0 || s->fold_mode > 3) { set_error("bad fold_mode %d", s->fold_mode); return SPEI_ERR_ARG; }
+  if (s->io_dtype != SPEI_IO_F32 && s->io_dtype != SPEI_IO_BF16) { set_error("bad io_dtype %d", s->io_dtype); return SPEI_ERR_ARG; }
   if (s->search != SPEI_SEARCH_TC && s->search != SPEI_SEARCH_EXACT && s->search != SPEI_SEARCH_TCS) {
     set_error("bad search %d", s->search); return SPEI_ERR_ARG;
   }
@@ -209,7 +211,7 @@ int spei_workspace_bytes(const SpeiShape* shape, size_t* bytes) {
   return SPEI_OK;
 }
 
-int spei_stage_norm(const SpeiShape* shape, const float* q, const float* k, void* workspace, size_t workspace_bytes,
+int spei_stage_norm(const SpeiShape* shape, const void* q, const void* k, void* workspace, size_t workspace_bytes,
                     void* stream) {
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
@@ -299,27 +301,27 @@ int spei_plan_info(const SpeiShape* shape, int32_t* out16) {
 // One pyramid level of the transfer.  lv1 (32 channels, 16-byte runs already) gathers straight from the
 // planar input; lv3 / lv2 gather from a channels-last copy (512-byte runs), which for lv3 is the fp32 copy
 // spei_stage_norm already made whenever ref_lv3 is the searched tensor itself (speinet.py:135).
-static int gather_level(const Plan& p, const SpeiShape* shape, int level, const int32_t* arg32, const float* ref, float* out,
-                        const float* staged_k, char* ws, cudaStream_t st) {
+static int gather_level(const Plan& p, const SpeiShape* shape, int level, const int32_t* arg32, const void* ref, void* out,
+                        const void* staged_k, char* ws, cudaStream_t st) {
   const int scale = level == 3 ? 1 : (level == 2 ? 2 : 4);
   const int c = level == 3 ? shape->c3 : (level == 2 ? shape->c2 : shape->c1);
   if (level == 1)
     return launch_gather_fold(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode, arg32, ref,
-                              out, st);
+                              out, p.io_bf16, st);
   const float* src;
   if (level == 3 && staged_k != nullptr && ref == staged_k) {
     src = (const float*)(ws + p.off_k32);
   } else {
     float* dst = (float*)(ws + (level == 3 ? p.off_ref3n : p.off_ref2n));
-    int rc = launch_stage_ref_nhwc(ref, shape->n * shape->rf, c, scale * shape->hr, scale * shape->wr, dst, st);
+    int rc = launch_stage_ref_nhwc(ref, p.io_bf16, shape->n * shape->rf, c, scale * shape->hr, scale * shape->wr, dst, st);
     if (rc) return rc;
     src = dst;
   }
   return launch_gather_fold_nhwc(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode, arg32, src,
-                                 out, st);
+                                 out, p.io_bf16, st);
 }
 
-int spei_gather_fold(const SpeiShape* shape, int level, const int32_t* arg32, const float* ref, float* out, const float* staged_k,
+int spei_gather_fold(const SpeiShape* shape, int level, const int32_t* arg32, const void* ref, void* out, const void* staged_k,
                      void* workspace, size_t workspace_bytes, void* stream) {
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
@@ -344,6 +346,22 @@ int spei_fuse_level(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, c
     return rc;
   if (out == dec || out == t) { set_error("fuse_level: out must not alias an input"); return SPEI_ERR_ARG; }
   return launch_fuse_level(n, c, h, w, scale, dec, t, S, weight, bias, out, (cudaStream_t)stream);
+}
+
+int spei_fuse_level_bf16(int32_t n, int32_t c, int32_t h, int32_t w, int32_t scale, const void* dec, const void* t,
+                         const float* S, const float* weight, const float* bias, void* out, void* stream) {
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  if (n < 1 || h < 1 || w < 1 || (scale != 1 && scale != 2 && scale != 4)) {
+    set_error("bad fuse_level dims n=%d h=%d w=%d scale=%d", n, h, w, scale); return SPEI_ERR_ARG;
+  }
+  if (c != 128 && c != 64 && c != 32) { set_error("fuse_level: c must be 128, 64 or 32 (got %d)", c); return SPEI_ERR_ARG; }
+  if ((rc = check_ptr(dec, "dec", 16)) || (rc = check_ptr(t, "t", 16)) || (rc = check_ptr(S, "S", 4)) ||
+      (rc = check_ptr(weight, "weight", 16)) || (rc = check_ptr(bias, "bias", 4)) || (rc = check_ptr(out, "out", 16)))
+    return rc;
+  if (out == dec || out == t) { set_error("fuse_level: out must not alias an input"); return SPEI_ERR_ARG; }
+  return launch_fuse_level_bf16(n, c, h, w, scale, dec, t, S, weight, bias, out, (cudaStream_t)stream);
 }
 
 int spei_rl_deconv(int32_t n, int32_t c, int32_t h, int32_t w, int32_t ks, int32_t num_iterations, float regularization_strength,
@@ -378,8 +396,8 @@ int spei_upsample2_bias_act(int32_t n, int32_t c, int32_t h, int32_t w, const fl
   return launch_upsample2_bias_act(n, c, h, w, y, bias, relu, out, (cudaStream_t)stream);
 }
 
-int spei_search_transfer(const SpeiShape* shape, const float* q, const float* k, const float* ref1, const float* ref2,
-                         const float* ref3, float* S, float* T3, float* T2, float* T1, int64_t* arg, int32_t* stats,
+int spei_search_transfer(const SpeiShape* shape, const void* q, const void* k, const void* ref1, const void* ref2,
+                         const void* ref3, float* S, void* T3, void* T2, void* T1, int64_t* arg, int32_t* stats,
                          void* workspace, size_t workspace_bytes, void* stream) {
   Plan p;
   int rc = prepare(shape, workspace, workspace_bytes, &p);
@@ -397,7 +415,7 @@ int spei_search_transfer(const SpeiShape* shape, const float* q, const float* k,
   // (b) SearchTransfer.py:33-34
   if ((rc = spei_relevance_argmax(shape, S, arg32, arg, stats, workspace, workspace_bytes, stream))) return rc;
   // (c) SearchTransfer.py:36-46
-  struct Lvl { const float* ref; float* out; int level; };
+  struct Lvl { const void* ref; void* out; int level; };
   const Lvl lv[3] = {{ref3, T3, 3}, {ref2, T2, 2}, {ref1, T1, 1}};
   for (const Lvl& l : lv) {
     if (!l.ref) continue;

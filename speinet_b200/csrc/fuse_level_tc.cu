@@ -26,6 +26,7 @@
 // issues the MMAs.  Three 16-channel stages, loads prefetched one 32-channel set ahead in registers, two to
 // three CTAs per SM.
 #include <cstdio>
+#include <cuda_bf16.h>
 
 #include "spei_common.cuh"
 #include "tc_ptx.cuh"
@@ -352,12 +353,19 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int C>
+// kBf16: dec / T / out are bf16 tensors (native bf16 I/O, north_star's 1e-2 mode).  A bf16 value is exactly representable in
+// TF32, so the activation split has no low part: the converter writes only the hi tile, the MMA issues 2 instead of 3
+// products per step (X.Wlo + X.Whi), the TMA boxes are half the bytes, and the epilogue updates / stores a bf16 box.
+// The arithmetic (fp32 weights split 3xTF32-style, fp32 accumulation, fp32 residual add, one rounding to bf16 at the
+// store) is exactly what the fp32 kernel computes on the up-cast inputs.
+template <int C, bool kBf16>
 __global__ void __launch_bounds__(FuseTsCfg<C>::kThreads, FuseTsCfg<C>::kCtasPerSm)
 fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_constant__ CUtensorMap tm_t,
                      const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ S,
                      const float* __restrict__ weight, const float* __restrict__ bias, int n_items, int h, int w, int scale) {
   using F = FuseTsCfg<C>;
+  constexpr uint32_t kRawTx = (kBf16 ? kFRawBytes / 2 : kFRawBytes) + F::kWBox;   // bytes one producer stage brings in
+  constexpr uint32_t kBoxTx = kBf16 ? F::kOutBox / 2 : F::kOutBox;               // bytes of a residual / output box
   constexpr int kRaw = F::kRaw, kU = F::kU, kE = F::kE, CW = F::kConvWarps, kConvThreads = CW * 32, NCH = F::NCH;
   constexpr int kCh = kFKC / F::kSplit;          // channels of a stage per converter thread (16 or 8)
   constexpr int K = 2 * C;
@@ -427,8 +435,14 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
         FPROF_T(pf_rfull, FUSE_WAIT(bar_rfull + 8 * r, (uint32_t)((g / kRaw) & 1), error_flag));
         const float* rbox = raw + (size_t)r * (F::kRawStage / 4);
         float x[kCh];
+        if (kBf16) {
+          const uint16_t* rb = reinterpret_cast<const uint16_t*>(rbox);
 #pragma unroll
-        for (int c = 0; c < kCh; ++c) x[c] = rbox[(part * kCh + c) * kFM + px];
+          for (int c = 0; c < kCh; ++c) x[c] = __uint_as_float((uint32_t)rb[(part * kCh + c) * kFM + px] << 16);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCh; ++c) x[c] = rbox[(part * kCh + c) * kFM + px];
+        }
         constexpr int kWChunks = kCh / 4;          // 16-byte chunks of weight row px this thread converts (C = 128 only)
         const int jrot = (px >> 1) & (kWChunks - 1);
         float4 wv[kWChunks];
@@ -465,7 +479,7 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) { hi[i] = xhi[8 * c8 + i]; lo[i] = xlo[8 * c8 + i]; }
           tc_st8(a_lane + (uint32_t)(u * 32 + 8 * c8), hi);
-          tc_st8(a_lane + (uint32_t)(u * 32 + 16 + 8 * c8), lo);
+          if (!kBf16) tc_st8(a_lane + (uint32_t)(u * 32 + 16 + 8 * c8), lo);   // bf16 activations: lo == 0, never read
         }
         if (!F::kResidentW && wrow) {
           const uint32_t b_hi = s0 + F::kOffB + (uint32_t)u * 2 * F::kBBytes, b_lo = b_hi + F::kBBytes;
@@ -506,8 +520,8 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
           for (uint32_t kk = 0; kk < kFKC / 8; ++kk) {
             const uint64_t dbh = umma_desc_kmajor(b_hi + kk * 2 * F::kBLBO, F::kBLBO, 128);
             const uint64_t dbl = umma_desc_kmajor(b_lo + kk * 2 * F::kBLBO, F::kBLBO, 128);
-            tc_mma_tf32_ts(d_tmem, a_lo + kk * 8, dbh, idesc, (kc | kk) != 0);  // small terms first
-            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, dbl, idesc, 1u);
+            if (!kBf16) tc_mma_tf32_ts(d_tmem, a_lo + kk * 8, dbh, idesc, (kc | kk) != 0);  // small terms first
+            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, dbl, idesc, kBf16 ? (uint32_t)((kc | kk) != 0) : 1u);
             tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, dbh, idesc, 1u);
           }
           tc_commit(bar_aempty + 8 * u);
@@ -529,7 +543,7 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
         for (int kc = 0; kc < NCH; ++kc, ++g) {
           const int r = g % kRaw;
           if (g >= kRaw) FPROF_T(pf_rempty, FUSE_WAIT(bar_rempty + 8 * r, (uint32_t)((g / kRaw - 1) & 1), error_flag));
-          mbar_arrive_expect_tx(bar_rfull + 8 * r, F::kRawStage);
+          mbar_arrive_expect_tx(bar_rfull + 8 * r, kRawTx);
           const int ch0 = kc * kFKC;
           tma_load_2d(s0 + r * F::kRawStage, ch0 < C ? &tm_dec : &tm_t, bar_rfull + 8 * r, p0, n * C + (ch0 < C ? ch0 : ch0 - C));
           if (!F::kResidentW) tma_load_2d(s0 + r * F::kRawStage + kFRawBytes, &tm_w, bar_rfull + 8 * r, ch0, 0);  // weight columns ch0..ch0+15
@@ -564,7 +578,7 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
       const int n = (int)(tl / tpi);
       const int p0 = (int)((tl - (long long)n * tpi) * kFM);
       const int e = (int)(pn % kE);
-      mbar_arrive_expect_tx(bar_efull + 8 * e, F::kOutBox);
+      mbar_arrive_expect_tx(bar_efull + 8 * e, kBoxTx);
       tma_load_2d(s0 + F::kOffOut + e * F::kOutBox, &tm_dec, bar_efull + 8 * e, p0, n * C + (int)(pn % kPasses) * kFOutCh);
     };
     if (elected) {
@@ -592,8 +606,17 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
         tc_ld16(taddr + c0, a);
         FPROF_T(pf_efull, FUSE_WAIT(bar_efull + 8 * e, (uint32_t)((pass / kE) & 1), error_flag));
         tc_wait_ld();
+        if (kBf16) {
+          uint16_t* ob = reinterpret_cast<uint16_t*>(ost);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ost[i * kFM + px] = ost[i * kFM + px] + (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
+          for (int i = 0; i < 16; ++i) {
+            const float v = __uint_as_float((uint32_t)ob[i * kFM + px] << 16) + (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
+            ob[i * kFM + px] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ost[i * kFM + px] = ost[i * kFM + px] + (__uint_as_float(a[i]) + __ldg(bias + c0 + i)) * sw;
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the TMA store (async proxy)
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (elected) {
@@ -622,29 +645,29 @@ fuse_level_ts_kernel(const __grid_constant__ CUtensorMap tm_dec, const __grid_co
   }
 }
 
-// 2-D map over an NCHW fp32 tensor seen as [n*C rows][plane]; box = 16 channels x 128 pixels
-static int make_plane_map(EncodeTiledFn enc, CUtensorMap* tm, const float* base, size_t rows, size_t plane) {
+// 2-D map over an NCHW fp32 (or bf16) tensor seen as [n*C rows][plane]; box = 16 channels x 128 pixels
+static int make_plane_map(EncodeTiledFn enc, CUtensorMap* tm, const void* base, size_t rows, size_t plane, bool bf16 = false) {
   const cuuint64_t dims[2] = {(cuuint64_t)plane, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)plane * 4};
+  const cuuint64_t strides[1] = {(cuuint64_t)plane * (bf16 ? 2 : 4)};
   const cuuint32_t box[2] = {kFM, kFKC};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  const CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
   return SPEI_OK;
 }
 
-template <int C>
-static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, const float* t, const float* S, const float* weight,
-                             const float* bias, float* out, cudaStream_t st) {
+template <int C, bool kBf16>
+static int launch_fuse_tma_t(int n, int h, int w, int scale, const void* dec, const void* t, const float* S, const float* weight,
+                             const float* bias, void* out, cudaStream_t st) {
   const size_t plane = (size_t)h * scale * w * scale;
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
   CUtensorMap tmd, tmt, tmw;
-  if ((rc = make_plane_map(enc, &tmd, dec, (size_t)n * C, plane))) return rc;
-  if ((rc = make_plane_map(enc, &tmt, t, (size_t)n * C, plane))) return rc;
+  if ((rc = make_plane_map(enc, &tmd, dec, (size_t)n * C, plane, kBf16))) return rc;
+  if ((rc = make_plane_map(enc, &tmt, t, (size_t)n * C, plane, kBf16))) return rc;
   {  // Conv2d 1x1 weight [C rows][2C] fp32; box = all C rows x 16 input channels
     const cuuint64_t dims[2] = {(cuuint64_t)(2 * C), (cuuint64_t)C};
     const cuuint64_t strides[1] = {(cuuint64_t)(2 * C) * 4};
@@ -656,15 +679,16 @@ static int launch_fuse_tma_t(int n, int h, int w, int scale, const float* dec, c
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fuse_level weight) failed with CUresult %d", (int)r); return SPEI_ERR_CUDA; }
   }
   const int smem = (int)FuseTsCfg<C>::kTotal;
-  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  SPEI_CUDA(cudaFuncSetAttribute(fuse_level_ts_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  auto kern = fuse_level_ts_kernel<C, kBf16>;
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   int dev = 0, sms = 0;
   SPEI_CUDA(cudaGetDevice(&dev));
   SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (long long)((plane + kFM - 1) / kFM) * n, slots = (long long)sms * FuseTsCfg<C>::kCtasPerSm;
   CUtensorMap tmo;
-  if ((rc = make_plane_map(enc, &tmo, out, (size_t)n * C, plane))) return rc;
-  fuse_level_ts_kernel<C><<<(unsigned)(tiles < slots ? tiles : slots), FuseTsCfg<C>::kThreads, smem, st>>>(tmd, tmt, tmw, tmo, S, weight, bias, n, h, w, scale);
+  if ((rc = make_plane_map(enc, &tmo, out, (size_t)n * C, plane, kBf16))) return rc;
+  kern<<<(unsigned)(tiles < slots ? tiles : slots), FuseTsCfg<C>::kThreads, smem, st>>>(tmd, tmt, tmw, tmo, S, weight, bias, n, h, w, scale);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }
@@ -692,13 +716,31 @@ int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, c
   // TMA needs 16-byte plane strides and 16-byte aligned bases; anything else takes the LDG-fed kernel
   const bool aligned = (((uintptr_t)dec | (uintptr_t)t | (uintptr_t)out | (uintptr_t)weight) & 15) == 0;
   if (aligned && plane % 4 == 0 && (long long)n * c < (1ll << 31) && plane < (1ull << 31)) {
-    if (c == 128) return launch_fuse_tma_t<128>(n, h, w, scale, dec, t, S, weight, bias, out, st);
-    if (c == 64) return launch_fuse_tma_t<64>(n, h, w, scale, dec, t, S, weight, bias, out, st);
-    if (c == 32) return launch_fuse_tma_t<32>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+    if (c == 128) return launch_fuse_tma_t<128, false>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+    if (c == 64) return launch_fuse_tma_t<64, false>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+    if (c == 32) return launch_fuse_tma_t<32, false>(n, h, w, scale, dec, t, S, weight, bias, out, st);
   }
   if (c == 128) return launch_fuse_tc_t<128>(n, h, w, scale, dec, t, S, weight, bias, out, st);
   if (c == 64) return launch_fuse_tc_t<64>(n, h, w, scale, dec, t, S, weight, bias, out, st);
   if (c == 32) return launch_fuse_tc_t<32>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  set_error("fuse_level: unsupported channel count %d", c);
+  return SPEI_ERR_ARG;
+}
+
+// bf16 dec / t / out (TMA-fed kernel only: planes must be a multiple of 8 pixels and the bases 16-byte aligned)
+int launch_fuse_level_bf16(int n, int c, int h, int w, int scale, const void* dec, const void* t, const float* S,
+                           const float* weight, const float* bias, void* out, cudaStream_t st) {
+  if (n > 65535) { set_error("fuse_level: n too large"); return SPEI_ERR_ARG; }
+  const size_t plane = (size_t)h * scale * w * scale;
+  const bool aligned = (((uintptr_t)dec | (uintptr_t)t | (uintptr_t)out | (uintptr_t)weight) & 15) == 0;
+  if (!aligned || plane % 8 != 0 || (long long)n * c >= (1ll << 31) || plane >= (1ull << 31)) {
+    set_error("fuse_level (bf16): planes must be a multiple of 8 pixels (got %zu) and every base 16-byte aligned; "
+              "up-cast to fp32 for other shapes", plane);
+    return SPEI_ERR_ARG;
+  }
+  if (c == 128) return launch_fuse_tma_t<128, true>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  if (c == 64) return launch_fuse_tma_t<64, true>(n, h, w, scale, dec, t, S, weight, bias, out, st);
+  if (c == 32) return launch_fuse_tma_t<32, true>(n, h, w, scale, dec, t, S, weight, bias, out, st);
   set_error("fuse_level: unsupported channel count %d", c);
   return SPEI_ERR_ARG;
 }

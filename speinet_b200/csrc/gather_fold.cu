@@ -45,12 +45,29 @@ __device__ const float4 g_zero16 = {0.f, 0.f, 0.f, 0.f};  // source of every non
 // round 1: 1.19 GB per launch).  Here the slowest grid dimension is an 8-channel slab (29.5 MB at 720p, L2 resident while
 // every query cell is processed for it), so DRAM sees each slab once; one block handles the S sub-rows of a cell row so the
 // index decode is shared by S x 8 x 32 outputs.
+// TIO = float, or __nv_bfloat16 for native bf16 I/O: a cell row is then an 8-byte run; the <= 9 terms are summed in fp32
+// in the same order and rounded to bf16 once at the store (= what the fp32 kernel followed by a cast produces).
+__device__ __forceinline__ float4 load_run4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load_run4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ void store_run4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void store_run4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  __stcs(reinterpret_cast<uint2*>(p), u);
+}
+
 // grid: (ceil(W/32), H, n * C/8)   block: (32 cells, 8 channels)
-template <int S, bool kCpuOrder, bool kTrueDiv>
+template <int S, bool kCpuOrder, bool kTrueDiv, typename TIO>
 __global__ void __launch_bounds__(256)
-gather_fold_slab_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int C,
+gather_fold_slab_kernel(const int32_t* __restrict__ arg, const TIO* __restrict__ ref, TIO* __restrict__ out, int rf, int C,
                         int H, int W, int Hr, int Wr) {
-  using V = typename Vec<S>::T;
+  static_assert(S == 4, "one thread = the 4 pixels of a cell row");
+  using V = float4;
   __shared__ long long s_off[9][32];  // per (neighbour, cell): float offset of the source run of sub-row 0, -1 = none
   const int X0 = blockIdx.x * 32, X = X0 + threadIdx.x;
   const int Y = blockIdx.y;
@@ -78,37 +95,42 @@ gather_fold_slab_kernel(const int32_t* __restrict__ arg, const float* __restrict
   }
   __syncthreads();
   if (X >= W) return;
-  const float* rbase = ref + (size_t)n * rf * C * ref_plane + (size_t)c * ref_plane;
-  const float* base[9];
+  const TIO* rbase = ref + (size_t)n * rf * C * ref_plane + (size_t)c * ref_plane;
+  const TIO* base[9];
   unsigned step[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const long long o = s_off[t][threadIdx.x];
-    base[t] = o >= 0 ? rbase + o : reinterpret_cast<const float*>(&g_zero16);
+    base[t] = o >= 0 ? rbase + o : reinterpret_cast<const TIO*>(&g_zero16);   // 16 zero bytes: zero in either type
     step[t] = o >= 0 ? (unsigned)ref_pitch : 0u;   // sub-row stride (0 for the zero constant)
   }
   const size_t out_plane = (size_t)(S * H) * (S * W);
-  float* obase = out + ((size_t)n * C + c) * out_plane + (size_t)(Y * S) * (S * W) + (size_t)X * S;
+  TIO* obase = out + ((size_t)n * C + c) * out_plane + (size_t)(Y * S) * (S * W) + (size_t)X * S;
 #pragma unroll
   for (int r = 0; r < S; ++r) {
     V v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = __ldg(reinterpret_cast<const V*>(base[t] + (size_t)r * step[t]));
+    for (int t = 0; t < 9; ++t) v[t] = load_run4(base[t] + (size_t)r * step[t]);
     V acc = vzero(V{});
 #pragma unroll
     for (int t = 0; t < 9; ++t) vadd(acc, v[t]);
-    __stcs(reinterpret_cast<V*>(obase + (size_t)r * (S * W)), fin<kTrueDiv>(acc));
+    store_run4(obase + (size_t)r * (S * W), fin<kTrueDiv>(acc));
   }
 }
 
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
-                       const float* ref, float* out, cudaStream_t st) {
+                       const void* ref, void* out, int io_bf16, cudaStream_t st) {
   if (c % 8) { set_error("gather_fold: channels must be a multiple of 8"); return SPEI_ERR_ARG; }
   if (scale != 4) { set_error("gather_fold (planar source): only the finest level (scale 4) takes this kernel"); return SPEI_ERR_ARG; }
   if ((long long)n * (c / 8) > 65535 || h > 65535) { set_error("gather_fold: grid too large (n * c / 8 = %lld)", (long long)n * (c / 8)); return SPEI_ERR_ARG; }
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
   const dim3 sgrid((w + 31) / 32, h, n * (c / 8)), block(32, 8);
-#define GFL(O_, D_) gather_fold_slab_kernel<4, O_, D_><<<sgrid, block, 0, st>>>(arg32, ref, out, rf, c, h, w, hr, wr)
+#define GFL(O_, D_)                                                                                                                  \
+  do {                                                                                                                               \
+    if (io_bf16) gather_fold_slab_kernel<4, O_, D_, __nv_bfloat16><<<sgrid, block, 0, st>>>(arg32, (const __nv_bfloat16*)ref,        \
+                                                                                           (__nv_bfloat16*)out, rf, c, h, w, hr, wr); \
+    else gather_fold_slab_kernel<4, O_, D_, float><<<sgrid, block, 0, st>>>(arg32, (const float*)ref, (float*)out, rf, c, h, w, hr, wr); \
+  } while (0)
   if (cpu_order) { if (true_div) GFL(true, true); else GFL(true, false); }
   else { if (true_div) GFL(false, true); else GFL(false, false); }
 #undef GFL

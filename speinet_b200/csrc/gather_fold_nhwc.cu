@@ -13,16 +13,17 @@
 
 namespace spei {
 
-// grid: (ceil(Ws/32), Hs, nimg)  block 256
+// grid: (ceil(Ws/32), Hs, nimg)  block 256.  TIn = float or __nv_bfloat16 (native bf16 I/O; the copy is fp32 either way)
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-stage_ref_nhwc_kernel(const float* __restrict__ x, int C, int Hs, int Ws, float* __restrict__ out) {
+stage_ref_nhwc_kernel(const TIn* __restrict__ x, int C, int Hs, int Ws, float* __restrict__ out) {
   extern __shared__ float tile[];  // [C][33]
   const int img = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t plane = (size_t)Hs * Ws;
-  const float* src = x + (size_t)img * C * plane + (size_t)y * Ws + x0;
+  const TIn* src = x + (size_t)img * C * plane + (size_t)y * Ws + x0;
   const bool in = (x0 + lane) < Ws;
-  for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = in ? __ldg(src + (size_t)c * plane + lane) : 0.f;
+  for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = in ? (float)src[(size_t)c * plane + lane] : 0.f;
   __syncthreads();
   float* dst = out + ((size_t)img * plane + (size_t)y * Ws + x0) * C;
   const int c4n = C >> 2;
@@ -36,23 +37,28 @@ stage_ref_nhwc_kernel(const float* __restrict__ x, int C, int Hs, int Ws, float*
   }
 }
 
-int launch_stage_ref_nhwc(const float* ref, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st) {
+int launch_stage_ref_nhwc(const void* ref, int in_bf16, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st) {
   if (nimg > 65535 || Hs > 65535) { set_error("stage_ref_nhwc: grid too large"); return SPEI_ERR_ARG; }
-  stage_ref_nhwc_kernel<<<dim3((Ws + 31) / 32, Hs, nimg), 256, C * 33 * sizeof(float), st>>>(ref, C, Hs, Ws, dst);
+  const dim3 grid((Ws + 31) / 32, Hs, nimg);
+  if (in_bf16) stage_ref_nhwc_kernel<<<grid, 256, C * 33 * sizeof(float), st>>>((const __nv_bfloat16*)ref, C, Hs, Ws, dst);
+  else stage_ref_nhwc_kernel<<<grid, 256, C * 33 * sizeof(float), st>>>((const float*)ref, C, Hs, Ws, dst);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }
 
 __device__ const float4 g_zero16n = {0.f, 0.f, 0.f, 0.f};  // source of every non-contributing neighbour
 
+__device__ __forceinline__ void store_out(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 template <bool kTrueDiv> __device__ __forceinline__ float ninth_n(float a) {
   return kTrueDiv ? __fdiv_rn(a, 9.0f) : __fmul_rn(a, 1.0f / 9.0f);
 }
 
 // grid: (ceil(W/32), H, n)  block 256; dynamic smem C * S * (32*S + 1) floats
-template <int S, int C, bool kCpuOrder, bool kTrueDiv>
+template <int S, int C, bool kCpuOrder, bool kTrueDiv, typename TOut>
 __global__ void __launch_bounds__(256)
-gather_fold_nhwc_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, float* __restrict__ out, int rf, int H,
+gather_fold_nhwc_kernel(const int32_t* __restrict__ arg, const float* __restrict__ ref, TOut* __restrict__ out, int rf, int H,
                         int W, int Hr, int Wr) {
   static_assert(S * (C / 4) == 32, "one warp covers one pixel row of one cell");
   constexpr int kPitch = 32 * S + 1;
@@ -117,25 +123,25 @@ gather_fold_nhwc_kernel(const int32_t* __restrict__ arg, const float* __restrict
   // write out: rows of 32*S consecutive pixels per (channel, pixel row)
   const int wpx = min(32, W - X0) * S;  // valid pixels in this tile row
   const size_t out_plane = (size_t)(S * H) * (S * W);
-  float* obase = out + (size_t)n * C * out_plane + (size_t)(Y * S) * (S * W) + (size_t)X0 * S;
+  TOut* obase = out + (size_t)n * C * out_plane + (size_t)(Y * S) * (S * W) + (size_t)X0 * S;
   for (int r = warp; r < C * S; r += 8) {
     const int c = r / S, ry = r - c * S;
     const float* trow = tile + (size_t)r * kPitch;
-    float* orow = obase + (size_t)c * out_plane + (size_t)ry * (S * W);
-    for (int xx = lane; xx < wpx; xx += 32) __stcs(orow + xx, trow[xx]);
+    TOut* orow = obase + (size_t)c * out_plane + (size_t)ry * (S * W);
+    for (int xx = lane; xx < wpx; xx += 32) store_out(orow + xx, trow[xx]);   // fp32: streaming store; bf16: one rounding of the fp32 sum
   }
 }
 
-template <int S, int C>
+template <int S, int C, typename TOut>
 static int launch_gf_nhwc_t(int n, int rf, int h, int w, int hr, int wr, int fold_mode, const int32_t* arg32, const float* ref,
-                            float* out, cudaStream_t st) {
+                            TOut* out, cudaStream_t st) {
   const int smem = C * S * (32 * S + 1) * (int)sizeof(float);
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
   dim3 grid((w + 31) / 32, h, n);
 #define GFN(O_, D_)                                                                                                   \
   do {                                                                                                                \
-    SPEI_CUDA(cudaFuncSetAttribute(gather_fold_nhwc_kernel<S, C, O_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    gather_fold_nhwc_kernel<S, C, O_, D_><<<grid, 256, smem, st>>>(arg32, ref, out, rf, h, w, hr, wr);               \
+    SPEI_CUDA(cudaFuncSetAttribute(gather_fold_nhwc_kernel<S, C, O_, D_, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    gather_fold_nhwc_kernel<S, C, O_, D_, TOut><<<grid, 256, smem, st>>>(arg32, ref, out, rf, h, w, hr, wr);         \
   } while (0)
   if (cpu_order) { if (true_div) GFN(true, true); else GFN(true, false); }
   else { if (true_div) GFN(false, true); else GFN(false, false); }
@@ -145,10 +151,15 @@ static int launch_gf_nhwc_t(int n, int rf, int h, int w, int hr, int wr, int fol
 }
 
 int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
-                            const float* ref_nhwc, float* out, cudaStream_t st) {
+                            const float* ref_nhwc, void* out, int out_bf16, cudaStream_t st) {
   if (n > 65535 || h > 65535) { set_error("gather_fold: grid too large"); return SPEI_ERR_ARG; }
-  if (scale == 1 && c == 128) return launch_gf_nhwc_t<1, 128>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, out, st);
-  if (scale == 2 && c == 64) return launch_gf_nhwc_t<2, 64>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, out, st);
+  if (out_bf16) {
+    if (scale == 1 && c == 128) return launch_gf_nhwc_t<1, 128>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, (__nv_bfloat16*)out, st);
+    if (scale == 2 && c == 64) return launch_gf_nhwc_t<2, 64>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, (__nv_bfloat16*)out, st);
+  } else {
+    if (scale == 1 && c == 128) return launch_gf_nhwc_t<1, 128>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, (float*)out, st);
+    if (scale == 2 && c == 64) return launch_gf_nhwc_t<2, 64>(n, rf, h, w, hr, wr, fold_mode, arg32, ref_nhwc, (float*)out, st);
+  }
   set_error("gather_fold (channels-last): unsupported scale/channels %d/%d", scale, c);
   return SPEI_ERR_ARG;
 }

@@ -70,6 +70,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return umma_desc_kmajor(saddr, lbo_bytes, kRowBytes);
 }
 
+template <bool kDebug>
 __global__ void __launch_bounds__(kThreads, 1)
 relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -245,7 +246,7 @@ relevance_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           v[4 * i4 + 2] = __uint_as_float(a[4 * i4 + 2]) * r.z;
           v[4 * i4 + 3] = __uint_as_float(a[4 * i4 + 3]) * r.w;
         }
-        if (p.debug_acc && pp == 0) {
+        if (kDebug && p.debug_acc && pp == 0) {   // compile-time: the production instantiation carries no debug branch
 #pragma unroll
           for (int i = 0; i < 16; ++i) p.debug_acc[(size_t)m * kAccCols + r2 * 16 + i] = __uint_as_float(a[i]);
         }
@@ -377,12 +378,12 @@ int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st) {
   tl_debug_acc = nullptr;
   SPEI_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int), st));
   // per device, so set it on every launch (nn.DataParallel replicas call from several devices)
-  SPEI_CUDA(cudaFuncSetAttribute(relevance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  auto kern = t.debug_acc ? relevance_tc_kernel<true> : relevance_tc_kernel<false>;
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   // ask for the largest shared-memory carve-out: the persistent CTA uses ~137 KB of it and the rest lets
   // kernels of other streams (rescoring / gather / fusion of the previous clip) co-reside on the SM
-  SPEI_CUDA(cudaFuncSetAttribute(relevance_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 (int)cudaSharedmemCarveoutMaxShared));
-  relevance_tc_kernel<<<p.G, kThreads, kSmemBytes, st>>>(tmq, tmk, t);
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  kern<<<p.G, kThreads, kSmemBytes, st>>>(tmq, tmk, t);
   SPEI_CUDA(cudaGetLastError());
   return SPEI_OK;
 }

@@ -51,6 +51,7 @@ struct OperandPlan {
 
 struct Plan {
   int mode;        // SPEI_SEARCH_TC (dense 9-tap MMA) or SPEI_SEARCH_TCS (tap-sharing); decides the operand tiling
+  int io_bf16;     // SpeiShape.io_dtype == SPEI_IO_BF16: q / k / ref* / T* are bf16 tensors
   int nlist;       // candidate lists per (query, key segment): 1 dense, 2 tap-sharing (two epilogue warp groups)
   int n, rf;
   int H, W, Hr, Wr;
@@ -83,7 +84,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // ---- stage launchers (defined in the .cu files) -----------------------------------------------
-int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st);
+int launch_stage_norm(const Plan& p, const void* q, const void* k, char* ws, cudaStream_t st);
 int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st);
 int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st);
 int tcs_epilogue_groups();   // candidate lists per (query, key segment) the tap-sharing kernel writes
@@ -106,10 +107,12 @@ constexpr float kWindowMargin = 1.0e-3f;
 __host__ __device__ inline float certified_window(float delta) { return delta + kWindowMargin; }
 int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st);
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
-                       const int32_t* arg32, const float* ref, float* out, cudaStream_t st);
-int launch_stage_ref_nhwc(const float* ref, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st);
+                       const int32_t* arg32, const void* ref, void* out, int io_bf16, cudaStream_t st);
+int launch_stage_ref_nhwc(const void* ref, int in_bf16, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st);
 int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
-                            const int32_t* arg32, const float* ref_nhwc, float* out, cudaStream_t st);
+                            const int32_t* arg32, const float* ref_nhwc, void* out, int out_bf16, cudaStream_t st);
+int launch_fuse_level_bf16(int n, int c, int h, int w, int scale, const void* dec, const void* t, const float* S,
+                           const float* weight, const float* bias, void* out, cudaStream_t st);
 int launch_fuse_level(int n, int c, int h, int w, int scale, const float* dec, const float* t, const float* S,
                       const float* weight, const float* bias, float* out, cudaStream_t st);
 // counters at workspace + off_counters (int32): [0, n) queries queued per item for the second pass; then

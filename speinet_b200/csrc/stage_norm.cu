@@ -23,7 +23,8 @@ constexpr int kPx = 32;  // pixels (consecutive x) per block
 
 // One operand (query set or key set) of the staging pass
 struct StageOp {
-  const float* x;          // [nimg][128][H][W] fp32
+  const void* x;           // [nimg][128][H][W] fp32, or bf16 when in_bf16 (native bf16 I/O: the staged bf16 operand is then exact)
+  int in_bf16;
   __nv_bfloat16* bf;       // [nimg][16][Vpad][Upad][8]
   float* x32;              // [nimg][H][W][128]
   float* ss;               // [nimg][H][W] per-pixel sum of squares
@@ -49,17 +50,23 @@ stage_transpose_kernel(const StageOp oq, const StageOp ok) {
   const int img = is_k ? blockIdx.z - oq.nimg : blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kPx;
   const int H = o.H, W = o.W;
   if (y >= H || x0 >= W) return;
-  const float* __restrict__ x = o.x;
+  const float* __restrict__ x = reinterpret_cast<const float*>(o.x);
+  const __nv_bfloat16* __restrict__ xb = reinterpret_cast<const __nv_bfloat16*>(o.x);
   __nv_bfloat16* __restrict__ bf = o.bf;
   float* __restrict__ x32 = o.x32;
   float* __restrict__ ss = o.ss;
   const int orient = o.orient, Upad = o.Upad, Vpad = o.Vpad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t plane = (size_t)H * W;
-  const float* src = x + (size_t)img * kC3 * plane + (size_t)y * W + x0;
+  const size_t soff = (size_t)img * kC3 * plane + (size_t)y * W + x0;
   const bool in = (x0 + lane) < W;
+  if (o.in_bf16) {
 #pragma unroll 4
-  for (int c = warp; c < kC3; c += 8) tile[c][lane] = in ? __ldg(src + (size_t)c * plane + lane) : 0.f;
+    for (int c = warp; c < kC3; c += 8) tile[c][lane] = in ? __bfloat162float(xb[soff + (size_t)c * plane + lane]) : 0.f;
+  } else {
+#pragma unroll 4
+    for (int c = warp; c < kC3; c += 8) tile[c][lane] = in ? __ldg(x + soff + (size_t)c * plane + lane) : 0.f;
+  }
   __syncthreads();
 
   // NHWC fp32 copy: 128 consecutive floats per pixel
@@ -187,10 +194,10 @@ zero_padding_kernel(const StageOp oq, const StageOp ok) {
   for (int pl = 0; pl < o.nimg * kCG; ++pl) *reinterpret_cast<uint4*>(o.bf + (pl * per + pos) * 8) = z;
 }
 
-static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* rs,
+static StageOp make_op(const void* x, int in_bf16, int nimg, int H, int W, const OperandPlan& o, __nv_bfloat16* bf, float* x32, float* ss, float* rs,
                        float* r, float* rkpad, float* d, int* dmax, int frames) {
   StageOp s{};
-  s.x = x; s.bf = bf; s.x32 = x32; s.ss = ss; s.rs = rs; s.r = r; s.rkpad = rkpad; s.d = d; s.dmax = dmax; s.frames = frames;
+  s.x = x; s.in_bf16 = in_bf16; s.bf = bf; s.x32 = x32; s.ss = ss; s.rs = rs; s.r = r; s.rkpad = rkpad; s.d = d; s.dmax = dmax; s.frames = frames;
   s.nimg = nimg; s.H = H; s.W = W; s.orient = o.orient; s.U = o.U; s.V = o.V; s.Upad = o.Upad; s.Vpad = o.Vpad;
   // dense tiling: [tv*Ny][tu*8]; tap-sharing tiling: [tv*Ny][Upad] with the staged image's 1-position u border
   const bool shared = o.tile_u == kSTileU;
@@ -198,11 +205,11 @@ static StageOp make_op(const float* x, int nimg, int H, int W, const OperandPlan
   return s;
 }
 
-int launch_stage_norm(const Plan& p, const float* q, const float* k, char* ws, cudaStream_t st) {
-  const StageOp oq = make_op(q, p.n, p.H, p.W, p.q, (__nv_bfloat16*)(ws + p.off_qbf), (float*)(ws + p.off_q32),
+int launch_stage_norm(const Plan& p, const void* q, const void* k, char* ws, cudaStream_t st) {
+  const StageOp oq = make_op(q, p.io_bf16, p.n, p.H, p.W, p.q, (__nv_bfloat16*)(ws + p.off_qbf), (float*)(ws + p.off_q32),
                              (float*)(ws + p.off_qss), (float*)(ws + p.off_qrs), (float*)(ws + p.off_rq), nullptr,
                              (float*)(ws + p.off_dq), nullptr, 1);
-  const StageOp ok = make_op(k, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
+  const StageOp ok = make_op(k, p.io_bf16, p.n * p.rf, p.Hr, p.Wr, p.k, (__nv_bfloat16*)(ws + p.off_kbf), (float*)(ws + p.off_k32),
                              (float*)(ws + p.off_kss), (float*)(ws + p.off_krs), (float*)(ws + p.off_rk), (float*)(ws + p.off_rkpad),
                              nullptr, (int*)(ws + p.off_dkmax), p.rf);
   if ((long long)oq.nimg + ok.nimg > 65535) { set_error("stage_norm: too many images"); return SPEI_ERR_ARG; }

@@ -28,6 +28,10 @@ def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torc
     `out`: optional preallocated contiguous fp32 result buffer (persistent buffers of a pipeline / CUDA graph)."""
     lib = _lib.load()
     out_dtype = dec.dtype
+    n_, c_, hs_, ws_ = dec.shape
+    if (dec.dtype == torch.bfloat16 and t.dtype == torch.bfloat16 and (out is None or out.dtype == torch.bfloat16)
+            and (hs_ * ws_) % 8 == 0 and dec.is_cuda and c_ in (32, 64, 128)):
+        return _fuse_level_bf16(lib, dec, t, S, weight, bias, scale, out)
     dec_f, t_f, S_f = dec.float().contiguous(), t.float().contiguous(), S.float().contiguous()
     w_f = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
     b_f = bias.detach().float().contiguous()
@@ -48,6 +52,30 @@ def fuse_level(dec: torch.Tensor, t: torch.Tensor, S: torch.Tensor, weight: torc
         rc = lib.spei_fuse_level(n, c, h, w, scale, _ptr(dec_f), _ptr(t_f), _ptr(S_f), _ptr(w_f), _ptr(b_f), _ptr(out), stream)
         _lib.check(rc, "spei_fuse_level")
     return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+
+def _fuse_level_bf16(lib, dec, t, S, weight, bias, scale, out=None):
+    """Native bf16 I/O: `spei_fuse_level_bf16` reads dec / t and writes the result as bf16 (fp32 accumulation)."""
+    dec_b, t_b = dec.contiguous(), t.contiguous()
+    S_f = S.float().contiguous()
+    w_f = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+    b_f = bias.detach().float().contiguous()
+    _check_inputs((dec_b, t_b, S_f))
+    n, c, hs, ws = dec_b.shape
+    h, w = S_f.shape[-2:]
+    if (hs, ws) != (h * scale, w * scale) or t_b.shape != dec_b.shape or tuple(w_f.shape) != (c, 2 * c):
+        raise RuntimeError(f"fuse_level: inconsistent shapes dec={tuple(dec.shape)} t={tuple(t.shape)} "
+                           f"S={tuple(S.shape)} weight={tuple(weight.shape)} scale={scale}")
+    dec_b, t_b, w_f = (x.clone() if x.data_ptr() % 16 else x for x in (dec_b, t_b, w_f))
+    with torch.cuda.device(dec_b.device):
+        if out is None:
+            out = torch.empty_like(dec_b)
+        elif out.shape != dec_b.shape or not out.is_contiguous() or out.device != dec_b.device or out.data_ptr() % 16:
+            raise RuntimeError(f"fuse_level: out must be a contiguous, 16-byte aligned bf16 tensor of shape {tuple(dec_b.shape)} on {dec_b.device}")
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dec_b.device).cuda_stream)
+        rc = lib.spei_fuse_level_bf16(n, c, h, w, scale, _ptr(dec_b), _ptr(t_b), _ptr(S_f), _ptr(w_f), _ptr(b_f), _ptr(out), stream)
+        _lib.check(rc, "spei_fuse_level_bf16")
+    return out
 
 
 def up2_conv1x1_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, relu: bool = True) -> torch.Tensor:

@@ -30,7 +30,7 @@ OUT_KEYS = ("S", "f3", "f2", "f1")
 class _Slot:
     def __init__(self):
         self.inp: Dict[str, torch.Tensor] = {}
-        self.out: Dict[str, torch.Tensor] = {}      # persistent fp32 result buffers: S, T3, T2, T1, arg, stats, f3, f2, f1
+        self.out: Dict[str, torch.Tensor] = {}      # persistent result buffers: S, T3, T2, T1, arg, stats, f3, f2, f1 (bf16 T / f for all-bf16 clips)
         self.fused: Dict[str, torch.Tensor] = {}    # what goes back to the host (S, f3, f2, f1 in the clip's dtype)
         self.graph = None
         self.sig = None
@@ -61,13 +61,17 @@ class HostPipeline:
         if sig != slot.sig:
             slot.inp = {k: torch.empty(clip[k].shape, dtype=clip[k].dtype, device=self.dev) for k in keys}
             n, c3, h, w = clip["q"].shape
+            # all-bf16 clips run the native bf16 kernels (T / fused features stay bf16 on the device); anything else is fp32
+            bf16 = all(clip[k].dtype == torch.bfloat16 for k in keys)
             f32 = dict(dtype=torch.float32, device=self.dev)
-            slot.out = {"S": torch.empty((n, 1, h, w), **f32), "T3": torch.empty((n, c3, h, w), **f32),
-                        "T2": torch.empty((n, c3 // 2, 2 * h, 2 * w), **f32), "T1": torch.empty((n, c3 // 4, 4 * h, 4 * w), **f32),
+            io = dict(dtype=torch.bfloat16 if bf16 else torch.float32, device=self.dev)
+            fo = io if (h * w) % 8 == 0 else f32          # the bf16 fusion kernel wants planes that are a multiple of 8 pixels
+            slot.out = {"S": torch.empty((n, 1, h, w), **f32), "T3": torch.empty((n, c3, h, w), **io),
+                        "T2": torch.empty((n, c3 // 2, 2 * h, 2 * w), **io), "T1": torch.empty((n, c3 // 4, 4 * h, 4 * w), **io),
                         "arg": torch.empty((n, h * w), dtype=torch.int64, device=self.dev),
                         "stats": torch.empty(8, dtype=torch.int32, device=self.dev),
-                        "f3": torch.empty((n, c3, h, w), **f32), "f2": torch.empty((n, c3 // 2, 2 * h, 2 * w), **f32),
-                        "f1": torch.empty((n, c3 // 4, 4 * h, 4 * w), **f32)}
+                        "f3": torch.empty((n, c3, h, w), **fo), "f2": torch.empty((n, c3 // 2, 2 * h, 2 * w), **fo),
+                        "f1": torch.empty((n, c3 // 4, 4 * h, 4 * w), **fo)}
             slot.fused = {}
             slot.graph, slot.sig, slot.warm = None, sig, False
         return slot.inp

@@ -32,15 +32,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _stack_frames(x: TensorOrList, name: str) -> torch.Tensor:
-    """[N,C,H,W] -> [N,1,C,H,W]; list of Rf such tensors or a 5-D tensor -> [N,Rf,C,H,W] (contiguous fp32)."""
+def _stack_frames(x: TensorOrList, name: str, dtype=torch.float32) -> torch.Tensor:
+    """[N,C,H,W] -> [N,1,C,H,W]; list of Rf such tensors or a 5-D tensor -> [N,Rf,C,H,W] (contiguous, `dtype`)."""
     if isinstance(x, (list, tuple)):
-        x = torch.stack([t.float() for t in x], dim=1)
+        x = torch.stack([t.to(dtype) for t in x], dim=1)
     elif x.dim() == 4:
         x = x.unsqueeze(1)
     elif x.dim() != 5:
         raise RuntimeError(f"{name}: expected a 4-D tensor, a 5-D [N,Rf,C,H,W] tensor or a list of 4-D tensors")
-    return x.float().contiguous()
+    return x.to(dtype).contiguous()
+
+
+def _first(x):
+    return x[0] if isinstance(x, (list, tuple)) else x
 
 
 def _check_inputs(tensors):
@@ -109,16 +113,22 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
     `eps` <= 0 (default): certified candidate window -- the bf16 tensor-core pass and the exact rescoring bracket the
     argmax with an error bound measured on the actual operands (include/speinet_b200.h, SpeiShape.eps); stats[6] counts
     violations of that bound (always 0; `SearchTransfer.check_certificate()` raises otherwise).  `eps` > 0: fixed window.
-    `out`: optional dict of preallocated fp32 outputs {"S", "T3", "T2", "T1", "arg", "stats"} to write into (persistent
-    buffers of a pipeline / CUDA graph); missing entries are allocated."""
+    `out`: optional dict of preallocated outputs {"S", "T3", "T2", "T1", "arg", "stats"} to write into (persistent
+    buffers of a pipeline / CUDA graph; S fp32, T* fp32 -- bf16 when every input is bf16 --, arg int64, stats int32 x 8);
+    missing entries are allocated."""
     lib = _lib.load()
     out_dtype = lrsr_lv3.dtype
-    q = lrsr_lv3.float().contiguous()
-    k = _stack_frames(refsr_lv3, "refsr_lv3")
+    # native bf16 I/O (SPEI_IO_BF16) when every feature tensor is bf16: the kernels read / write bf16 themselves; any other
+    # mix (fp16, partly bf16) is up-cast to fp32 here and the outputs cast back
+    tensors = [_first(t) for t in (lrsr_lv3, refsr_lv3, ref_lv1, ref_lv2, ref_lv3) if t is not None]
+    native_bf16 = all(t.dtype == torch.bfloat16 for t in tensors)
+    io = torch.bfloat16 if native_bf16 else torch.float32
+    q = lrsr_lv3.to(io).contiguous()
+    k = _stack_frames(refsr_lv3, "refsr_lv3", io)
     same3 = ref_lv3 is refsr_lv3
-    r3 = k if same3 else (_stack_frames(ref_lv3, "ref_lv3") if ref_lv3 is not None else None)
-    r2 = _stack_frames(ref_lv2, "ref_lv2") if ref_lv2 is not None else None
-    r1 = _stack_frames(ref_lv1, "ref_lv1") if ref_lv1 is not None else None
+    r3 = k if same3 else (_stack_frames(ref_lv3, "ref_lv3", io) if ref_lv3 is not None else None)
+    r2 = _stack_frames(ref_lv2, "ref_lv2", io) if ref_lv2 is not None else None
+    r1 = _stack_frames(ref_lv1, "ref_lv1", io) if ref_lv1 is not None else None
     _check_inputs([t for t in (q, k, r1, r2, r3) if t is not None])
     n, c3, h, w = q.shape
     nk, rf, ck, hr, wr = k.shape
@@ -130,7 +140,8 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
     # the C-ABI wants 16-byte aligned bases (TMA / vector loads): a contiguous view at an odd storage offset is cloned
     q, k, r1, r2, r3 = (t.clone() if t is not None and t.data_ptr() % 16 else t for t in (q, k, r1, r2, r3))
     shape = _lib.SpeiShape(n=n, h=h, w=w, hr=hr, wr=wr, rf=rf, c3=c3, c2=c3 // 2, c1=c3 // 4,
-                           fold_mode=_FOLD[fold_mode], search=_SEARCH[search], eps=float(eps))
+                           fold_mode=_FOLD[fold_mode], search=_SEARCH[search], eps=float(eps),
+                           io_dtype=_lib.IO_BF16 if native_bf16 else _lib.IO_F32)
     dev = q.device
     out = out or {}
 
@@ -147,9 +158,9 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
         slot = _WS.get(dev, ws_bytes, cur)
         ws_ptr = (slot["buf"].data_ptr() + 255) // 256 * 256
         S = buf("S", (n, 1, h, w))
-        T3 = buf("T3", (n, c3, h, w)) if r3 is not None else None
-        T2 = buf("T2", (n, c3 // 2, 2 * h, 2 * w)) if r2 is not None else None
-        T1 = buf("T1", (n, c3 // 4, 4 * h, 4 * w)) if r1 is not None else None
+        T3 = buf("T3", (n, c3, h, w), io) if r3 is not None else None
+        T2 = buf("T2", (n, c3 // 2, 2 * h, 2 * w), io) if r2 is not None else None
+        T1 = buf("T1", (n, c3 // 4, 4 * h, 4 * w), io) if r1 is not None else None
         arg = buf("arg", (n, h * w), torch.int64)
         stats = buf("stats", (_lib.STATS_WORDS,), torch.int32)
         rc = lib.spei_search_transfer(ctypes.byref(shape), _ptr(q), _ptr(k), _ptr(r1), _ptr(r2), _ptr(r3), _ptr(S),
@@ -158,7 +169,7 @@ def search_transfer(lrsr_lv3: torch.Tensor, refsr_lv3: TensorOrList, ref_lv1: Te
         _lib.check(rc, "spei_search_transfer")
         _WS.release(slot, cur)
     if out_dtype != torch.float32:  # bf16 / fp16 callers get their dtype back; arithmetic stayed fp32
-        S, T3, T2, T1 = (t.to(out_dtype) if t is not None else None for t in (S, T3, T2, T1))
+        S, T3, T2, T1 = (t.to(out_dtype) if t is not None and t.dtype != out_dtype else t for t in (S, T3, T2, T1))
     return S, T3, T2, T1, arg, stats
 
 

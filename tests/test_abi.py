@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_table_matches_header(lib):
     from speinet_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert ctypes.sizeof(_lib.SpeiShape) == 12 * 4
+    assert ctypes.sizeof(_lib.SpeiShape) == 13 * 4
 
 
 def test_version_and_error_string(lib):

@@ -191,3 +191,30 @@ def test_bf16_inputs_full_size_within_1e2(cfg):
         got = speinet_b200.fuse_level(dec, T, S, wt, b, s)
         assert got.dtype == torch.bfloat16
         torch.testing.assert_close(got.float().permute(1, 0, 2, 3)[:, ok], want.permute(1, 0, 2, 3)[:, ok], **tol(want))
+
+
+@pytest.mark.parametrize("hw", [(180, 320), (23, 31)])
+def test_native_bf16_kernels_equal_the_upcast_fp32_path(hw):
+    """Native bf16 I/O (SPEI_IO_BF16, spei_fuse_level_bf16) against the fp32 kernels on the up-cast inputs with the outputs
+    cast to bf16: same arithmetic (bf16 operands are exact in the search, fp32 sums, one rounding at the store), so indices,
+    S, the transferred pyramids and the fused features must be BIT-identical.  (23, 31): ragged tiles, odd plane at lv3."""
+    h, w = hw
+    q, lv3, lv2, lv1 = (t if isinstance(t, torch.Tensor) else t[0] for t in make_features("image_like", 1, h, w, 1, seed=3))
+    q, lv3, lv2, lv1 = (t.bfloat16() for t in (q, lv3, lv2, lv1))
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        S, T3, T2, T1, arg = st(q, lv3, lv1, lv2, lv3, return_index=True)                     # native bf16
+        fS, f3, f2, f1, farg = st(q.float(), lv3.float(), lv1.float(), lv2.float(), lv3.float(), return_index=True)
+    assert all(t.dtype == torch.bfloat16 for t in (S, T3, T2, T1))
+    assert torch.equal(arg, farg) and torch.equal(S, fS.bfloat16())
+    for a, b in ((T3, f3), (T2, f2), (T1, f1)):
+        assert torch.equal(a, b.bfloat16())
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for lvl, T, s in ((3, T3, 1), (2, T2, 2), (1, T1, 4)):
+        ch = T.shape[1]
+        dec = (torch.randn(T.shape, device="cuda", generator=g) * 0.3).bfloat16()
+        wt = torch.randn(ch, 2 * ch, 1, 1, device="cuda", generator=g) * (2 * ch) ** -0.5
+        b = torch.randn(ch, device="cuda", generator=g) * 0.1
+        got = speinet_b200.fuse_level(dec, T, fS, wt, b, s)                                   # native when the plane is a multiple of 8
+        want = speinet_b200.fuse_level(dec.float(), T.float(), fS, wt, b, s).bfloat16()
+        assert got.dtype == torch.bfloat16 and torch.equal(got, want), f"lv{lvl}"
