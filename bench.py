@@ -557,6 +557,29 @@ def run_ours(args, rank, world, local_rank):
                     "note": "inputs = the fp32 step's inputs rounded to bf16; difference includes that input rounding (north_star bar 1e-2)"}
         del Pb, db
 
+    # ---- the other BASELINE.json configurations through the drop-in module (parity for them: tests/test_gpu_fullsize.py) ----
+    other = None
+    if rank == 0 and not args.no_other:
+        other = {}
+        st_mod = speinet_b200.SearchTransfer().to(dev)
+        gq = torch.Generator(device=dev).manual_seed(77)
+        rn = lambda *sh, std: torch.randn(*sh, device=dev, generator=gq) * std
+        for name, (nb, hh, ww, rf) in (("configs[3] BSD 640x480, 2 sharp frames, batch 8", (8, 120, 160, 2)),
+                                       ("configs[0] 256x256 clip (module only)", (1, 64, 64, 1)),
+                                       ("720p batch 4", (4, H, W, 1))):
+            qq = rn(nb, C3, hh, ww, std=0.2)
+            l3 = [rn(nb, C3, hh, ww, std=0.04) for _ in range(rf)]
+            l2 = [rn(nb, C3 // 2, 2 * hh, 2 * ww, std=0.04) for _ in range(rf)]
+            l1 = [rn(nb, C3 // 4, 4 * hh, 4 * ww, std=0.04) for _ in range(rf)]
+            a3, a2, a1 = (x if rf > 1 else x[0] for x in (l3, l2, l1))
+            with torch.no_grad():
+                t = timed_ms(lambda: st_mod(qq, a3, a1, a2, a3), iters=5)
+            flops = 2.0 * nb * (hh * ww) * (rf * hh * ww) * 9 * C3
+            other[name] = {"ms_per_call": t, "items_per_s": nb * 1e3 / t, "algorithmic_relevance_TFLOP": flops / 1e12,
+                           "algorithmic_PFLOPs": flops / (t * 1e-3) / 1e15, "stats": dict(zip(_lib.STATS_NAMES, st_mod.last_stats.cpu().tolist()))}
+            del qq, l3, l2, l1, a3, a2, a1
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public API with host buffers (speinet_b200.HostPipeline: H2D, compute and
     # D2H of consecutive clips overlap on three streams; every clip's copies are inside the timed region) ----
     from speinet_b200.pipeline import HostPipeline
@@ -675,7 +698,7 @@ def run_ours(args, rank, world, local_rank):
                                        "achieved": FLOPS_RELEVANCE / (dense["candidates_ms"] * 1e-3) / 1e12,
                                        "frac": FLOPS_RELEVANCE / (dense["candidates_ms"] * 1e-3) / 1e12 / peak_burst} if dense else None),
                      "traffic": traffic, "traffic_source": traffic_src},
-        "e2e": e2e, "e2e_bf16_io": e2e_bf16, "bf16_io_device_resident": bf16_leg,
+        "e2e": e2e, "e2e_bf16_io": e2e_bf16, "bf16_io_device_resident": bf16_leg, "other_configs_module_call": other,
         "gpu_launches": sum(KERNELS_PER_STEP.values()) * args.steps, "gpu_launches_per_step": KERNELS_PER_STEP,
         "clocks": clocks,
         "search_stats_last_step": dict(zip(_lib.STATS_NAMES, P.stats.cpu().tolist())), "plan": plan,
@@ -808,6 +831,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs only; not a valid bench line)")
     ap.add_argument("--no-graph", action="store_true", help="host-buffer leg without CUDA graphs")
     ap.add_argument("--no-bf16", action="store_true", help="skip the native bf16 I/O leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the timing of the other BASELINE configurations")
     ap.add_argument("--no-sweep", action="store_true", help="N > 1: skip the 64-clip sweep and the row-band leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
