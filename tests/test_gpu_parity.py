@@ -747,3 +747,53 @@ def test_integration_md_ctypes_stub_matches_module():
     import runpy
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runpy.run_path(os.path.join(root, "tools", "check_integration_stub.py"), run_name="__main__")
+
+
+# ------------------------------------------------------------------ multi-GPU (needs >= 2 devices) ------
+def _peer_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ok = True
+        for num_clips in (world, 2 * world):              # one clip per rank per exchange, then two
+            mine = speinet_b200.shard_clips(num_clips, rank, world)
+            pg = speinet_b200.PeerGather((3, 8, 16), num_clips, rank, world, device=torch.device("cuda", rank))
+            for rnd in range(4):                            # reuse of both slots, result() before the next push()
+                local = torch.stack([torch.full((3, 8, 16), float(100 * rnd + c), device="cuda") for c in mine])
+                slot = pg.push(local)
+                got = pg.result(slot)
+                want = speinet_b200.gather_outputs(local, num_clips, rank, world)      # NCCL all-gather of the same shards
+                ok = ok and bool(torch.equal(got, want)) and got[:, 0, 0, 0].tolist() == [float(100 * rnd + c) for c in range(num_clips)]
+        # row bands of one frame: stitched result equals the unsharded module (NCCL gather_rows)
+        torch.manual_seed(5)
+        q = torch.randn(1, 128, 22, 20, device="cuda") * 0.2
+        lv3 = torch.randn(1, 128, 22, 20, device="cuda") * 0.04
+        lv2 = torch.randn(1, 64, 44, 40, device="cuda") * 0.04
+        lv1 = torch.randn(1, 32, 88, 80, device="cuda") * 0.04
+        st = speinet_b200.SearchTransfer().cuda()
+        with torch.no_grad():
+            parts = speinet_b200.gather_rows(speinet_b200.search_transfer_rows(st, q, lv3, lv1, lv2, lv3, rank, world), 22, rank, world)
+            full = st(q, lv3, lv1, lv2, lv3)
+        ok = ok and all(bool(torch.equal(a, b)) for a, b in zip(parts, full))
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_gather_and_row_bands_on_two_gpus():
+    """PeerGather (NVLink peer memory, copy engines) against NCCL's all-gather, and the NCCL row-band gather of one frame,
+    one process per GPU.  Skipped on single-GPU boxes (bench.py --gpus N runs the same checks at N = 2 .. 8)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_peer_worker, args=(2, port, ret), nprocs=2, join=True)
+        assert ret[0] and ret[1]
