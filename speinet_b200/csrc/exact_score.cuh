@@ -22,28 +22,36 @@ __device__ __forceinline__ unsigned long long pack_score(float s, int j) {
 __device__ __forceinline__ float packed_score(unsigned long long b) { return unflip_f32((unsigned)(b >> 32)); }
 __device__ __forceinline__ int packed_key(unsigned long long b) { return (int)(0xffffffffu - (unsigned)(b & 0xffffffffull)); }
 
-// The warp's query patch sits in `qv` (tap t, channels 4*lane .. 4*lane+3 at qv[t * 32]; zero for taps outside the image);
-// kimg is the NHWC fp32 image of the key's reference frame.  Each lane owns 4 channels of every tap: their 4 products are
-// summed in fp32 (one rounding of ~6e-8 relative per product, ~2e-9 absolute on a normalised score -- four orders of
-// magnitude inside the 1e-5 near-tie rule) and the 9 tap partials, then the 32 lanes, are accumulated in fp64 in a fixed
-// order.  Returns the same value in every lane.
-__device__ __forceinline__ float exact_relevance(const float4* __restrict__ qv, const float* __restrict__ kimg, int hr, int wr, int Hr,
-                                                 int Wr, float rq, float rk, int lane) {
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // three independent chains (taps t % 3)
+// The warp's query patch is read through `qtap(t)`: a pointer to the 32 float4 (128 channels) of tap t, zero for taps outside
+// the image (lane l reads channels 4l .. 4l+3); kimg is the NHWC fp32 image of the key's reference frame.  Each lane owns 4
+// channels of every tap: their 4 products are summed in fp32 (one rounding of ~6e-8 relative per product, ~2e-9 absolute on
+// a normalised score -- four orders of magnitude inside the 1e-5 near-tie rule) and the 9 tap partials, then the 32 lanes,
+// are accumulated in fp64 in a fixed order.  Returns the same value in every lane.
+template <typename QTap>
+__device__ __forceinline__ float exact_relevance(QTap qtap, const float* __restrict__ kimg, int hr, int wr, int Hr, int Wr, float rq,
+                                                 float rk, int lane) {
+  // all nine key rows are requested before the first one is used (branch-free: a tap outside the image re-reads the centre
+  // row and is zeroed); the kernel is latency bound, so loads in flight are what matters
+  const float4* kc = reinterpret_cast<const float4*>(kimg) + ((size_t)hr * Wr + wr) * (kC3 / 4) + lane;
+  float4 kv[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    const int yy = hr + t / 3 - 1, xx = wr + t % 3 - 1;
-    if (yy >= 0 && yy < Hr && xx >= 0 && xx < Wr) {
-      const float4 kv = __ldg(reinterpret_cast<const float4*>(kimg + ((size_t)yy * Wr + xx) * kC3) + lane);
-      const float4 qq = qv[t * 32];
-      float part = qq.x * kv.x;
-      part = fmaf(qq.y, kv.y, part);
-      part = fmaf(qq.z, kv.z, part);
-      part = fmaf(qq.w, kv.w, part);
-      if (t % 3 == 0) acc0 += (double)part;
-      else if (t % 3 == 1) acc1 += (double)part;
-      else acc2 += (double)part;
-    }
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    const bool in = (unsigned)(hr + dy) < (unsigned)Hr && (unsigned)(wr + dx) < (unsigned)Wr;
+    kv[t] = __ldg(kc + (in ? (dy * Wr + dx) * (kC3 / 4) : 0));
+    if (!in) kv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // three independent chains (taps t % 3), fixed order
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 qq = qtap(t)[lane];
+    float part = qq.x * kv[t].x;
+    part = fmaf(qq.y, kv[t].y, part);
+    part = fmaf(qq.z, kv[t].z, part);
+    part = fmaf(qq.w, kv[t].w, part);
+    if (t % 3 == 0) acc0 += (double)part;
+    else if (t % 3 == 1) acc1 += (double)part;
+    else acc2 += (double)part;
   }
   double acc = (acc0 + acc1) + acc2;
 #pragma unroll

@@ -362,8 +362,8 @@ rescore_emitted_kernel(const FlagParams p) {
     const float rk = __ldg(p.rk + ((size_t)item * p.rf + f) * p.lk1 + rem);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]) + lane;
-    const float score = exact_relevance(qv, p.k32 + ((size_t)item * p.rf + f) * p.lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
+    const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]);
+    const float score = exact_relevance([&](int t) { return qv + t * 32; }, p.k32 + ((size_t)item * p.rf + f) * p.lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
     if (lane == 0) atomicMax(p.packed + qid, pack_score(score, jj));
     ++nres;
   }

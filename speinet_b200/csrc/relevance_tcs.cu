@@ -395,7 +395,13 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         }
         const float thr = fmax3(tv[kTopK - 1], tv[0] - winq, floor0);
         const float bound = smax > 0.f ? smax * rk_s[128 + (r - r_lo)] : 0.f;   // NaN (no key of the row in the image) fails the test
-        if (qlin >= 0 && bound > thr) {
+#ifdef SPEI_TCS_NOSLOW    // timing experiment only (wrong results): tap sums + row maximum, never the insertion path
+        tv[0] = fmaxf(tv[0], bound);
+        if (false)
+#else
+        if (qlin >= 0 && bound > thr)
+#endif
+        {
           float v[32];
           const float* rkr = rk_s + (r - r_lo) * 32;
 #pragma unroll

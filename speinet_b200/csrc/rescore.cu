@@ -21,7 +21,9 @@
 
 namespace spei {
 
+// persistent CTA that owns tile pair p (the split of relevance_tc*.cu); 32-bit arithmetic whenever (P + 1) * G fits
 __host__ __device__ inline long long cta_of_pair_d(long long p, long long P, int G) {
+  if ((P + 1) * (long long)G < (1ll << 32)) return (long long)(((unsigned)(p + 1) * (unsigned)G - 1u) / (unsigned)P);
   return ((p + 1) * (long long)G - 1) / P;
 }
 
@@ -45,20 +47,37 @@ struct RescoreParams {
   int32_t* stats;
 };
 
-__global__ void __launch_bounds__(256, 4)
+// Query block of one CTA: kRB x kRB queries, one warp each.  Their 3x3 patches overlap, so the block stages the
+// (kRB + 2)^2 pixel rows (512 B each) it needs ONCE in shared memory -- 1.15 KB per query instead of the 4.6 KB a private
+// patch costs; the kernel is bound by L2 -> SM traffic (every exact score also reads the 4.6 KB key patch).
+constexpr int kRB = 4, kRBH = kRB + 2;
+
+// grid: (ceil(W / 4), ceil(H / 4), n)   block: 512 (16 warps)
+__global__ void __launch_bounds__(kRB * kRB * 32, 2)
 rescore_kernel(const RescoreParams p) {
-  // L2-bandwidth bound (each exact score reads the 4.6 KB key patch): written for occupancy and early issue -- the
-  // query's 9x128 patch goes to shared memory with cp.async (no register staging, <= 64 registers -> 32 warps per SM)
-  // and every load that does not depend on another is issued before the first branch.
-  __shared__ __align__(16) float qpatch[8][9 * kC3];
+  __shared__ __align__(16) float qrows[kRBH * kRBH][kC3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long wq = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const int L = p.H * p.W;
-  if (wq >= (long long)p.n * L) return;
-  const int n = (int)(wq / L), ql = (int)(wq % L);
-  const int y = ql / p.W, x = ql % p.W;
+  const int n = blockIdx.z, y0 = blockIdx.y * kRB, x0 = blockIdx.x * kRB;
+  {  // halo rows of the block, zero-filled outside the image (= the zero padding of F.unfold)
+    const float* qimg = p.q32 + (size_t)n * L * kC3;
+    for (int e = threadIdx.x; e < kRBH * kRBH * 32; e += kRB * kRB * 32) {
+      const int row = e >> 5, l4 = e & 31;
+      const int yy = y0 + row / kRBH - 1, xx = x0 + row % kRBH - 1;
+      const bool in = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const float* src = qimg + ((size_t)(in ? yy : 0) * p.W + (in ? xx : 0)) * kC3 + l4 * 4;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(&qrows[row][l4 * 4]);
+      const int sz = in ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int wy = warp / kRB, wx = warp % kRB;
+  const int y = y0 + wy, x = x0 + wx;
+  const bool live = y < p.H && x < p.W;
+  const int ql = live ? y * p.W + x : 0;
+  const long long wq = (long long)n * L + ql;
   const int lk1 = p.Hr * p.Wr;
-  load_query_patch_async(&qpatch[warp][0], p.q32 + (size_t)n * L * kC3, y, x, p.H, p.W, lane);
 
   // which query tile is this, and into how many key segments was it split?
   const int u = p.q_orient == 0 ? x : y, v = p.q_orient == 0 ? y : x;
@@ -70,25 +89,18 @@ rescore_kernel(const RescoreParams p) {
   const float* cv = p.cval + (size_t)wq * p.maxseg * p.nlist * kTopK;
   const int32_t* ci = p.cidx + (size_t)wq * p.maxseg * p.nlist * kTopK;
 
-  // independent loads first: patch energy (zero test), query norm, residual bound, first 32 candidates
-  float s = 0.f;
-  {
-    const float* ss = p.qss + (size_t)n * L;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) s += __ldg(ss + yy * p.W + xx);
-    }
-  }
+  // independent loads first: query norm (+inf marks an all-zero patch, stage_norm.cu), residual bound, first 32 candidates
   const float rq = __ldg(p.rq + wq);
   const float delta = p.eps > 0.f ? 0.f : certified_delta(__ldg(p.dq + wq), __int_as_float(__ldg(p.dkmax + n)));
   int j0 = -1;
   float v0 = 0.f;
   if (lane < ncand) { j0 = __ldg(ci + lane); v0 = __ldg(cv + lane); }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();   // the block's query rows are in shared memory (no block-wide barrier after this point)
+  if (!live) return;
 
   // zero query patch: every relevance is 0 -> first index, S = 0 (reference semantics)
-  if (s == 0.f) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (rq == INFINITY) {
     if (lane == 0) {
       p.S[wq] = 0.f; p.arg32[wq] = 0;
       if (p.arg64) p.arg64[wq] = 0;
@@ -110,13 +122,13 @@ rescore_kernel(const RescoreParams p) {
     const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
     if (ob > bn || (ob == bn && (unsigned)oj < (unsigned)bj)) { bn = ob; bj = oj; }   // (unsigned): -1 loses
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-  const float4* qv = reinterpret_cast<const float4*>(&qpatch[warp][0]) + lane;  // tap t at qv[t * 32]
+  auto qtap = [&](int t) {   // tap (t / 3, t % 3) of this warp's query = block row (wy + t / 3, wx + t % 3)
+    return reinterpret_cast<const float4*>(&qrows[(wy + t / 3) * kRBH + wx + t % 3][0]);
+  };
   auto exact = [&](int jj) {
     const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
     const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
-    return exact_relevance(qv, p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
+    return exact_relevance(qtap, p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
   };
   // every query has at least one candidate: its lists hold the best keys of every segment (bj >= 0)
   const float E = exact(bj);
@@ -223,6 +235,7 @@ exact_search_kernel(const ExactParams p) {
     const int r = qb + ty * 4 + i;
     cq[i] = r < nq ? (p.list ? __ldg(p.list + (size_t)n * L + r) : r) : -1;
     crq[i] = cq[i] >= 0 ? __ldg(p.rq + (size_t)n * L + cq[i]) : 0.f;
+    if (crq[i] == INFINITY) crq[i] = 0.f;   // all-zero query patch (marked by stage_norm.cu): every relevance is 0 -> first index
   }
   unsigned long long best[4] = {0ull, 0ull, 0ull, 0ull};
 
@@ -379,8 +392,8 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   r.flag_list = (int32_t*)(ws + p.off_flag); r.counters = (int32_t*)(ws + p.off_counters);
   r.thr = (float*)(ws + p.off_thr); r.packed = (unsigned long long*)(ws + p.off_packed);
   r.stats = stats;
-  const long long nq = (long long)p.n * p.H * p.W;
-  rescore_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(r);
+  if ((p.H + kRB - 1) / kRB > 65535) { set_error("rescore: grid too large"); return SPEI_ERR_ARG; }
+  rescore_kernel<<<dim3((p.W + kRB - 1) / kRB, (p.H + kRB - 1) / kRB, p.n), kRB * kRB * 32, 0, st>>>(r);
   SPEI_CUDA(cudaGetLastError());
 
   // queued queries (saturated candidate lists): second tcgen05 pass enumerating every key at or above each query's
@@ -393,8 +406,10 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   e.enable = r.counters + p.n + kCntExhaust;
   const int L = p.H * p.W, qblocks = (L + kEQ - 1) / kEQ;
   const int max_splits = (p.rf * p.Hr * p.Wr + kEK - 1) / kEK;
-  e.key_splits = max_splits < 148 ? max_splits : 148;
-  exact_search_kernel<<<dim3(qblocks < 16 ? qblocks : 16, e.key_splits, p.n), 256, 0, st>>>(e);
+  // (a small grid: this launch is idle in every ordinary call and only has to exit quickly; when it does run, the
+  // grid-stride loops cover any queue length)
+  e.key_splits = max_splits < 74 ? max_splits : 74;
+  exact_search_kernel<<<dim3(qblocks < 8 ? qblocks : 8, e.key_splits, p.n), 256, 0, st>>>(e);
   SPEI_CUDA(cudaGetLastError());
   unpack_kernel<<<dim3(148, 1, p.n), 256, 0, st>>>(e.packed, e.list, e.list_count, L, S, arg32, arg64);
   SPEI_CUDA(cudaGetLastError());

@@ -17,9 +17,13 @@ constexpr int kTileU = 8;         // tile extent along the fast (contiguous) ima
 constexpr int kQTileV = 16;       // query tile: 8 x 16 positions = 128 MMA rows
 constexpr int kMaxNy = 32;        // key tile: 8 x Ny positions = up to 256 MMA columns
 #ifndef SPEI_TOPK
-#define SPEI_TOPK 16
+#define SPEI_TOPK 8
 #endif
-constexpr int kTopK = SPEI_TOPK;  // bf16-pass candidates kept per query per key segment (multiple of 4)
+// bf16-pass candidates kept per query, key segment and epilogue group (multiple of 4).  8 since round 2: a list that cannot
+// hold a query's in-window keys is no longer a 133-MFLOP exhaustive search but a slot in the second tcgen05 pass, so the
+// shorter sorted insertion wins (720p, certified window: randn -1 %, image-like features -7 %, x16 low-noise -10 % of
+// search + exactness time against 16; profiles/r02_window_cost.json)
+constexpr int kTopK = SPEI_TOPK;
 // tap-sharing search (relevance_tcs.cu): tiles are 32 wide along u (30 interior + a 1-position halo each side,
 // the u taps are summed in the epilogue), queries 4 rows, keys up to 8 rows
 constexpr int kSTileU = 30;       // interior tile extent along u

@@ -142,7 +142,9 @@ patch_norms_kernel(const StageOp oq, const StageOp ok) {
     const size_t plane = (size_t)o.H * o.W;
     const int img = (int)(i / plane), rem = (int)(i % plane);
     const float s = patch_sum(o.ss + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
-    o.r[i] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    // F.normalize: v / max(||v||, 1e-12).  An all-zero QUERY patch is marked with +inf (the rescoring short-circuits it to
+    // S = 0, arg = 0 -- every relevance is 0 and torch.max returns the first index; nothing else multiplies by it)
+    o.r[i] = (s == 0.f && o.dmax == nullptr) ? INFINITY : 1.0f / fmaxf(sqrtf(s), 1e-12f);
     // relative rounding residual of the patch (the 1 % factor of certified_delta() covers the fp32 sums, sqrt and division)
     const float sr = patch_sum(o.rs + (size_t)img * plane, o.H, o.W, rem / o.W, rem % o.W);
     const float dl = s > 0.f ? fminf(sqrtf(sr / s), 1.f) : 0.f;
