@@ -2,7 +2,7 @@
 # ncu evidence for the bench command (B200_PROFILING.md recipe): plain run first, then the launch
 # list, then full captures of the dominant kernel and (KERNELS=...) of the secondary ones.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-bf16 --no-other"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list exit $?"
@@ -13,6 +13,6 @@ echo "full capture (tcgen05) exit $?"
 fi
 if [ -n "$KERNELS" ]; then
   $CMD > gpurun_out/ncu_plain3.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 40 -c 12 -o gpurun_out/prof_rest $CMD > gpurun_out/ncu_full_rest.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 6 -c 18 -o gpurun_out/prof_rest $CMD > gpurun_out/ncu_full_rest.log 2>&1
   echo "full capture (rest) exit $?"
 fi
