@@ -65,7 +65,7 @@ constexpr uint32_t kSStageBytesMax = kCGS * (kSMaxNy + 2) * kSRowBytes;       //
 constexpr uint32_t kSStagesPerTile = kCG / kCGS;                              // 4
 constexpr uint32_t kSNumBars = 2 * kSStages + 6;
 constexpr uint32_t kSRkOffset = kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8 + 16;  // per epilogue warp: 128 floats + row maxima
-constexpr uint32_t kSRkWarpFloats = 132;  // [<=4 rows][32] reciprocal key norms + 4 row maxima
+constexpr uint32_t kSRkWarpFloats = 144;  // [<=4 rows][32] reciprocal key norms + [<=4 rows][4] maxima over 8-column groups
 constexpr uint32_t kSSmemBytes = kSRkOffset + 4 * kSGroups * kSRkWarpFloats * 4;
 static_assert(kSRkOffset % 16 == 0, "key-norm staging must be float4 aligned");
 constexpr uint32_t kSTmemCols = 512;
@@ -296,16 +296,17 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       const int ku0 = kc.tu * kSTileU - 1, kv0 = kc.tv * p.Ny;
       // largest reciprocal norm of every key row (NaN = keys outside the image are ignored by fmaxf): the row test
       // below bounds all 30 scores of a row by (largest tap sum) x (largest reciprocal norm)
+      // (four lanes hold the 8 columns of a group: rows lane >> 4 (+2), group (lane & 15) >> 2)
       float rmax0 = fmaxf(pre[0].x, pre[0].y), rmax1 = fmaxf(pre[1].x, pre[1].y);
 #pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) {
+      for (int o = 2; o >= 1; o >>= 1) {
         rmax0 = fmaxf(rmax0, __shfl_xor_sync(0xffffffffu, rmax0, o));
         rmax1 = fmaxf(rmax1, __shfl_xor_sync(0xffffffffu, rmax1, o));
       }
       __syncwarp();
       reinterpret_cast<float2*>(rk_s)[lane] = pre[0];
       reinterpret_cast<float2*>(rk_s)[lane + 32] = pre[1];
-      if ((lane & 15) == 0) { rk_s[128 + (lane >> 4)] = rmax0; rk_s[130 + (lane >> 4)] = rmax1; }
+      if ((lane & 3) == 0) { rk_s[128 + (lane >> 2)] = rmax0; rk_s[136 + (lane >> 2)] = rmax1; }
       __syncwarp();
       const PairIdx nx = next_pair(ix, p.QT, p.KT);
       const KeyTile kn = key_tile_next(kc, p.k_tu, p.k_tvn, p.rf);
@@ -385,16 +386,20 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         // Row test on the un-normalised tap sums: score[i] = s[i] * rk[i] <= max(s) * max(rk) when max(s) > 0 and
         // <= 0 otherwise (rk > 0), so a row whose bound does not beat the entry bar holds no candidate and its key
         // norms are never read (one broadcast LDS + 16 FMNMX instead of 8 LDS.128 + 16 FMUL2 + 16 FMNMX per row).
-        float smax;
+        // ... per group of 8 columns: half as many rows take the slow path as with one bound per row (round-2 A/B)
+        float gb[4], bound;
         {
-          const float m0 = fmax3(s[1], s[2], s[3]), m1 = fmax3(s[4], s[5], s[6]), m2 = fmax3(s[7], s[8], s[9]);
-          const float m3 = fmax3(s[10], s[11], s[12]), m4 = fmax3(s[13], s[14], s[15]), m5 = fmax3(s[16], s[17], s[18]);
-          const float m6 = fmax3(s[19], s[20], s[21]), m7 = fmax3(s[22], s[23], s[24]), m8 = fmax3(s[25], s[26], s[27]);
-          const float m9 = fmax3(s[28], s[29], s[30]);
-          smax = fmaxf(fmax3(fmax3(m0, m1, m2), fmax3(m3, m4, m5), fmax3(m6, m7, m8)), m9);
+          const float g0 = fmax3(fmax3(s[1], s[2], s[3]), fmax3(s[4], s[5], s[6]), s[7]);
+          const float g1 = fmax3(fmax3(s[8], s[9], s[10]), fmax3(s[11], s[12], s[13]), fmaxf(s[14], s[15]));
+          const float g2 = fmax3(fmax3(s[16], s[17], s[18]), fmax3(s[19], s[20], s[21]), fmaxf(s[22], s[23]));
+          const float g3 = fmax3(fmax3(s[24], s[25], s[26]), fmax3(s[27], s[28], s[29]), s[30]);
+          const float4 gm = *reinterpret_cast<const float4*>(rk_s + 128 + (r - r_lo) * 4);   // broadcast read
+          // a non-positive maximum bounds its group's scores by 0; a NaN product (no key of the group inside the image)
+          // fails every comparison and is dropped by fmaxf
+          gb[0] = fmaxf(g0, 0.f) * gm.x; gb[1] = fmaxf(g1, 0.f) * gm.y; gb[2] = fmaxf(g2, 0.f) * gm.z; gb[3] = fmaxf(g3, 0.f) * gm.w;
+          bound = fmaxf(fmaxf(gb[0], gb[1]), fmaxf(gb[2], gb[3]));
         }
         const float thr = fmax3(tv[kTopK - 1], tv[0] - winq, floor0);
-        const float bound = smax > 0.f ? smax * rk_s[128 + (r - r_lo)] : 0.f;   // NaN (no key of the row in the image) fails the test
 #ifdef SPEI_TCS_NOSLOW    // timing experiment only (wrong results): tap sums + row maximum, never the insertion path
         tv[0] = fmaxf(tv[0], bound);
         if (false)
@@ -402,33 +407,37 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         if (qlin >= 0 && bound > thr)
 #endif
         {
-          float v[32];
+          // compact slow path: only the 8-column groups whose bound passed are multiplied out (products s * rk, NaN for
+          // keys outside the image) and compared -> bit mask of the qualifying columns (halo columns 0 / 31 excluded), then
+          // one sorted insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
           const float* rkr = rk_s + (r - r_lo) * 32;
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 t4 = reinterpret_cast<const float4*>(rkr)[i4];  // broadcast reads
-            fmul2(v[4 * i4], v[4 * i4 + 1], s[4 * i4], s[4 * i4 + 1], t4.x, t4.y);  // NaN for keys outside the image
-            fmul2(v[4 * i4 + 2], v[4 * i4 + 3], s[4 * i4 + 2], s[4 * i4 + 3], t4.z, t4.w);
-          }
-          // compact slow path: bit mask of the qualifying columns (halo columns 0 / 31 excluded), then one sorted
-          // insertion per set bit.  Strict '>' keeps earlier keys ahead on ties.
           unsigned msk = 0;
 #pragma unroll
-          for (int i = 1; i < 31; ++i) msk |= (v[i] > thr) ? (1u << i) : 0u;
+          for (int g = 0; g < 4; ++g) {
+            if (gb[g] > thr) {
+              const float4 ta = reinterpret_cast<const float4*>(rkr)[2 * g], tb = reinterpret_cast<const float4*>(rkr)[2 * g + 1];
+              const float rk8[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int i = 8 * g + j;
+                if (i >= 1 && i <= 30) msk |= (s[i] * rk8[j] > thr) ? (1u << i) : 0u;
+              }
+            }
+          }
           while (msk) {
             const int i = __ffs(msk) - 1;
             msk &= msk - 1;
             // 32-way register select as a 5-level tree on the bits of i
             float s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s16[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+            for (int j = 0; j < 16; ++j) s16[j] = (i & 1) ? s[2 * j + 1] : s[2 * j];
 #pragma unroll
             for (int j = 0; j < 8; ++j) s8[j] = (i & 2) ? s16[2 * j + 1] : s16[2 * j];
 #pragma unroll
             for (int j = 0; j < 4; ++j) s4[j] = (i & 4) ? s8[2 * j + 1] : s8[2 * j];
 #pragma unroll
             for (int j = 0; j < 2; ++j) s2[j] = (i & 8) ? s4[2 * j + 1] : s4[2 * j];
-            float x = (i & 16) ? s2[1] : s2[0];
+            float x = ((i & 16) ? s2[1] : s2[0]) * rkr[i];   // the same fp32 product the mask compared
             if (x > fmax3(tv[kTopK - 1], tv[0] - winq, floor0)) {
               int xi = f * p.lk1 + uv_to_linear(p.k_orient, ku0 + i, kv0 + r, p.Wr);
 #pragma unroll
