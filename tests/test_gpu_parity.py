@@ -799,3 +799,32 @@ def test_peer_memory_gather_and_row_bands_on_two_gpus():
         ret = mgr.dict()
         mp.spawn(_peer_worker, args=(2, port, ret), nprocs=2, join=True)
         assert ret[0] and ret[1]
+
+
+def test_misaligned_views_take_a_working_path():
+    """Contiguous views whose storage offset is not a multiple of 16 bytes (e.g. x[1:] of an odd-sized plane): the search
+    wrapper clones them, the fusion entry point routes them to its LDG-fed kernel -- no RuntimeError, same results
+    (round-1 ADVICE: such views used to be rejected)."""
+    torch.manual_seed(19)
+    h, w = 9, 13                                           # odd planes: every slice below starts at an odd float offset
+    big_q = torch.randn(2, 128, h, w, device="cuda") * 0.2
+    big_k = torch.randn(2, 128, h, w, device="cuda") * 0.04
+    big2 = torch.randn(2, 64, 2 * h, 2 * w, device="cuda") * 0.04
+    big1 = torch.randn(2, 32, 4 * h, 4 * w, device="cuda") * 0.04
+    flat = torch.randn(128 * h * w + 1, device="cuda") * 0.2
+    q_odd = flat[1:].view(1, 128, h, w)                    # data_ptr % 16 == 4
+    assert q_odd.data_ptr() % 16 != 0 and q_odd.is_contiguous()
+    st = speinet_b200.SearchTransfer().cuda()
+    with torch.no_grad():
+        got = st(q_odd, big_k[1:], big1[1:], big2[1:], big_k[1:])
+        want = st(q_odd.clone(), big_k[1:].clone(), big1[1:].clone(), big2[1:].clone(), big_k[1:].clone())
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    S, T3 = got[0], got[1]
+    wt = torch.randn(128, 256, 1, 1, device="cuda") * 0.05
+    b = torch.randn(128, device="cuda")
+    dflat = torch.randn(128 * h * w + 3, device="cuda")
+    dec_odd = dflat[3:].view(1, 128, h, w)
+    assert dec_odd.data_ptr() % 16 != 0
+    f_odd = speinet_b200.fuse_level(dec_odd, T3, S, wt, b, 1)
+    f_ref = speinet_b200.fuse_level(dec_odd.clone(), T3.clone(), S, wt, b, 1)
+    torch.testing.assert_close(f_odd, f_ref, rtol=1e-5, atol=1e-6)   # (LDG-fed vs TMA-fed kernel when the plane allows TMA)
