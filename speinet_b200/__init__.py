@@ -6,10 +6,10 @@ host-side mirror of the reference interface (`SearchTransfer`, `SelfTransfer`, `
 """
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .search_transfer import SearchTransfer, SelfTransfer, search_transfer  # noqa: F401
-from .fusion import fuse_level, up2_conv1x1_act, decode_fused, install  # noqa: F401
+from .fusion import fuse_level, up2_conv1x1_act, decode_fused, forward_sync_free, install  # noqa: F401
 from .sharding import shard_clips, gather_outputs, PeerGather, row_band, search_transfer_rows, gather_rows  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 from .rl_deconv import create_blur_kernel, r_l_per_channel  # noqa: F401
 
-__all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "up2_conv1x1_act", "decode_fused", "install",
+__all__ = ["SearchTransfer", "SelfTransfer", "search_transfer", "fuse_level", "up2_conv1x1_act", "decode_fused", "forward_sync_free", "install",
            "shard_clips", "gather_outputs", "PeerGather", "HostPipeline", "create_blur_kernel", "r_l_per_channel", "load_library", "LIB_PATH"]

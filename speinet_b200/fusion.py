@@ -128,7 +128,35 @@ def decode_fused(net, f_fusion, weight_S, sharp_lv3, sharp_lv2, sharp_lv1):
     return rn.outBlock(f_lv1)                                                                           # :120
 
 
-def install(net, fuse: bool = True, edge_prior: bool = True, **search_kwargs):
+def forward_sync_free(net, x, has_sharp=None):
+    """`SPEINet.forward` (speinet.py:150-168) without its device->host round trips.
+
+    The reference decides per batch row which branch runs by testing frame 3 for all-zeros ON THE DEVICE and then uses the
+    boolean masks in `.any()`, `x[mask]` and `out[mask] = ...` -- four host synchronisations per call (`_forwardx`, :70-73,
+    :155, :162).  The caller of the inference loop zeroes that frame itself (inference_SPEINet.py:385-388), so it already
+    knows: pass `has_sharp` (one bool per batch row, True = frame 3 is a real sharp frame -> `_forwardbs`, False ->
+    `_forwardb`) and no synchronisation is left.  With `has_sharp=None` the mask is computed as in the reference and read
+    back ONCE.  Rows are routed with index tensors built on the host; the result equals `net.forward(x)`."""
+    n = x.shape[0]
+    if has_sharp is None:
+        zeros4 = torch.all(x[:, 3].reshape(n, -1) == 0, dim=1)          # :71 (frame 4's test, :72, is never used)
+        has_sharp = [not z for z in zeros4.tolist()]                      # the one read-back
+    if len(has_sharp) != n:
+        raise ValueError(f"has_sharp has {len(has_sharp)} entries for a batch of {n}")
+    rows_b = [i for i, hs in enumerate(has_sharp) if not hs]
+    rows_bs = [i for i, hs in enumerate(has_sharp) if hs]
+    if not rows_b:
+        return net._forwardbs(x)
+    if not rows_bs:
+        return net._forwardb(x)
+    out = torch.empty((n, x.shape[2], x.shape[3], x.shape[4]), device=x.device, dtype=x.dtype)
+    for rows, fn in ((rows_b, net._forwardb), (rows_bs, net._forwardbs)):
+        idx = torch.tensor(rows, device=x.device)
+        out.index_copy_(0, idx, fn(x.index_select(0, idx)))
+    return out
+
+
+def install(net, fuse: bool = True, edge_prior: bool = True, sync_free_forward: bool = False, **search_kwargs):
     """Swap the B200 hot path into a reference-style SPEINet instance (speinet.py:53-54,92).
 
     With `edge_prior`, the module that defines the network class gets its global `r_l_per_channel`
@@ -137,7 +165,8 @@ def install(net, fuse: bool = True, edge_prior: bool = True, **search_kwargs):
 
     `net.SearchTransfer` / `net.SelfTransfer` are replaced by the modules of this package (weights of
     their unused/used 1x1 convs are carried over, so a strict checkpoint load done before or after
-    still works) and, if `fuse`, `net._decode` is rebound to `decode_fused`."""
+    still works) and, if `fuse`, `net._decode` is rebound to `decode_fused`.  `sync_free_forward` rebinds `net.forward` to
+    `forward_sync_free` (same result, one device->host read instead of four; `net(x, has_sharp=[...])` removes that one too)."""
     dev = next(net.parameters()).device
     new_st = SearchTransfer(**search_kwargs).to(dev)
     new_st.load_state_dict(net.SearchTransfer.state_dict())
@@ -148,6 +177,8 @@ def install(net, fuse: bool = True, edge_prior: bool = True, **search_kwargs):
         net.SelfTransfer = new_self
     if fuse:
         net._decode = types.MethodType(decode_fused, net)
+    if sync_free_forward:
+        net.forward = types.MethodType(forward_sync_free, net)
     if edge_prior:
         import sys
         from .rl_deconv import r_l_per_channel

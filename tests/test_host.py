@@ -173,3 +173,49 @@ def test_install_on_the_real_reference_speinet_swaps_modules_and_keeps_checkpoin
             os.environ.pop("CUDA_VISIBLE_DEVICES", None)
         else:
             os.environ["CUDA_VISIBLE_DEVICES"] = env_before
+
+
+def test_forward_sync_free_equals_reference_forward_on_a_mixed_batch():
+    """`forward_sync_free` against the reference's own `SPEINet.forward` (CPU, import shims, tiny Swin): a batch whose rows
+    take different branches (frame 3 zero / non-zero), with the mask given by the caller and derived on the device."""
+    import importlib.util
+    import sys
+    import types
+    ref = os.environ.get("SPEINET_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "model")):
+        pytest.skip("reference not mounted")
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mk_golden_model2", os.path.join(here, "golden", "make_golden_model.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    mk.install_shims()
+    env_before = os.environ.get("CUDA_VISIBLE_DEVICES")
+    saved_modules = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.")}
+    saved_cuda = torch.Tensor.cuda
+    sys.path.insert(0, ref)
+    try:
+        from model import speinet as ref_speinet
+        torch.Tensor.cuda = lambda self, *a, **k: self       # rcl.py:29-30 calls .cuda() unconditionally
+        torch.manual_seed(0)
+        args = types.SimpleNamespace(patch_size=32, window_size=4, rgb_range=1, depths=[1], embed_dim=32, num_heads=[2],
+                                     mlp_ratio=2, resi_connection="1conv", n_colors=3, n_sequence=3, n_resblock=1, n_feat=32, cpu=True)
+        net = ref_speinet.SPEINet(in_channels=3, n_sequence=3, out_channels=3, n_resblock=1, n_feat=32, device="cpu", args=args).eval()
+        x = torch.rand(3, 5, 3, 32, 32)
+        x[1, 3] = 0                                             # row 1 has no sharp frame -> SelfTransfer branch
+        with torch.no_grad():
+            want = net(x)
+            got_given = speinet_b200.forward_sync_free(net, x, has_sharp=[True, False, True])
+            got_derived = speinet_b200.forward_sync_free(net, x)
+            all_sharp = speinet_b200.forward_sync_free(net, x[[0, 2]], has_sharp=[True, True])
+        assert torch.equal(got_given, want) and torch.equal(got_derived, want)
+        assert torch.equal(all_sharp, want[[0, 2]])
+    finally:
+        torch.Tensor.cuda = saved_cuda
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_modules)
+        if env_before is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = env_before
