@@ -15,11 +15,12 @@
 // positions u = 0 and u = 31 of a tile are halo (consumed, not produced), so tiles advance by 30: 120
 // of 128 rows and 30 of 32 columns per key row are productive, and the tensor-core work drops
 // 3 * (30/32)^2 = 2.6x against the dense kernel for identical bf16 scores (same products, fp32 sums).
-// What bounds the kernel (round-1 measurements, profiles/r01_tcs_ablation.md): the chip runs it at its power cap
-// (sw_power_cap, 1.6-1.75 GHz), so time tracks the work done rather than one saturated unit.  MMA + TMA alone
-// (epilogue stubbed out) take 1.69 ms; TMEM loads add nothing; the epilogue arithmetic adds ~0.5 ms, of which the
-// 60 shuffles per key row are ~0.15 ms.  ncu: shared-memory data pipe 50 % LSU (shuffles) + 41 % tensor-core
-// operand reads, tensor pipe 55-60 % active.
+// What bounds the kernel (round-2 measurements): the epilogue, and it is dispatch bound.  Ablation
+// ladder at 720p: MMA + TMA only 1.69 ms; + TMEM loads 1.71; + tap-sum adds, maxima, bookkeeping 1.85; + the 60 lane
+// shuffles per key row 2.08; + the insertion path 2.27 (kTopK 16, one bound per row) -> 2.15 ms with kTopK 8 and the
+// per-group row test below.  More epilogue warps are slower, the query operand from tensor memory is slower (2.71 ms),
+// tcgen05.shift / lane-offset tcgen05.ld cannot replace the shuffles (tools/exp/).  The chip also runs the kernel at its
+// power cap (sw_power_cap, 1.67-1.75 GHz); tensor pipe 62 % active.
 //
 // Operand layout: the same channel-group-planar bf16 images as the dense kernel ([16][Vpad][Upad][8],
 // zero border).  A tile row is exactly 32 positions x 16 B = 512 B, so the canonical no-swizzle
@@ -32,9 +33,9 @@
 //   warp 2    TMEM allocator (2 x 256 columns, double-buffered accumulators)
 //   warps 4-11 epilogue, two groups of four (warp % 4 = the tile row v it owns): group h handles key rows
 //             [h*ceil(Ny/2), ...) of every tile and keeps its own top-k list per query (the rescoring merges lists).
-//             Per key row: 2 TMEM loads, 60 shuffles + 32 packed adds (tap sums), a 30-way max, and ONE test of
-//             max(tap sum) x max(reciprocal key norm of the row) against the entry bar; only rows that pass read
-//             their key norms and go through the sorted insertion.  The first tile of a list is swept twice: the
+//             Per key row: 2 TMEM loads, 60 shuffles + 32 packed adds (tap sums), maxima over four 8-column groups and ONE
+//             test of max_g(max(tap sum of group g) x max(reciprocal key norm of group g)) against the entry bar; only rows
+//             that pass multiply out the groups that passed and go through the sorted insertion.  The first tile of a list is swept twice: the
 //             first sweep only finds its best score, which seeds the entry bar.  (Alternating whole tiles between
 //             the groups was tried and is slower: each accumulator is then held for a full 8-row epilogue.)
 #include <cuda.h>
