@@ -234,23 +234,25 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
     long long qlin = -1;
     float winq = 0.f, floor0 = -INFINITY;
     float* rk_s = reinterpret_cast<float*>(smem + kSRkOffset) + (warp - 4) * kSRkWarpFloats;  // this warp's key norms: [<=4 rows][32]
-    // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=4 rows][32] reciprocal norms
+    // key-norm prefetch: lane l owns float2 #l and #(l+32) of the warp's [<=4 rows][32] reciprocal norms.  32-bit element
+    // offsets (the launcher checks the array fits) and lane-invariant parts hoisted: the 64-bit address chain of the
+    // round-1 form was ~45 instructions per tile per warp
+    const int pf_row = lane >> 4;                                    // rows pf_row and pf_row + 2
+    const bool pf_ok0 = r_lo + pf_row < r_hi, pf_ok1 = r_lo + pf_row + 2 < r_hi;
+    const uint32_t pf_off0 = (uint32_t)(pf_row * p.UkP + (lane & 15) * 2), pf_off1 = pf_off0 + 2u * (uint32_t)p.UkP;
     auto rk_prefetch = [&](int item, const KeyTile kt, float2 (&pre)[2]) {
-      const float* base = p.rkpad + ((size_t)(item * p.rf + kt.f) * p.VkT + kt.tv * p.Ny + r_lo) * p.UkP + kt.tu * kSTileU;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int e2 = lane + 32 * j, row = e2 >> 4;
-        pre[j] = (r_lo + row) < r_hi ? __ldg(reinterpret_cast<const float2*>(base + (size_t)row * p.UkP) + (e2 & 15))
-                                     : make_float2(0.f, 0.f);
-      }
+      const uint32_t off = (uint32_t)(((item * p.rf + kt.f) * p.VkT + kt.tv * p.Ny + r_lo) * p.UkP + kt.tu * kSTileU);
+      const float* base = p.rkpad + off;
+      pre[0] = pf_ok0 ? __ldg(reinterpret_cast<const float2*>(base + pf_off0)) : make_float2(0.f, 0.f);
+      pre[1] = pf_ok1 ? __ldg(reinterpret_cast<const float2*>(base + pf_off1)) : make_float2(0.f, 0.f);
     };
-    // tap sums of one key row from the two TMEM loads: (m-1, col-1) + (m, col) + (m+1, col+1).  Columns 0 and 31 are
-    // halo (their sums are computed on garbage neighbours and never looked at); packed f32x2 adds.
-    auto tap_sums = [&](const uint32_t (&a)[16], const uint32_t (&c)[16], float (&s)[32]) {
+    // tap sums of one key row from its 32 accumulator columns: (m-1, col-1) + (m, col) + (m+1, col+1).  Columns 0 and 31
+    // are halo: s[0] / s[31] are never looked at and simply alias the raw entries.  Packed f32x2 adds for columns 2..29;
+    // columns 1 and 30 take scalar adds (same rounding order) so that no zero has to be moved into a register pair.
+    auto tap_sums = [&](const uint32_t (&xr)[32], float (&s)[32]) {
       float x[32], up[32], dn[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { x[i] = __uint_as_float(a[i]); x[16 + i] = __uint_as_float(c[i]); }
-      up[0] = 0.f; dn[0] = 0.f; up[31] = 0.f; dn[31] = 0.f;
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(xr[i]);
 #pragma unroll
       for (int i = 1; i < 31; ++i) {
 #ifdef SPEI_TCS_NOSHFL   // timing experiment only (wrong sums): what the lane exchange costs
@@ -261,8 +263,12 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         dn[i] = __shfl_down_sync(0xffffffffu, x[i + 1], 1);
 #endif
       }
+      s[0] = x[0];
+      s[31] = x[31];
+      s[1] = __fadd_rn(__fadd_rn(up[1], dn[1]), x[1]);
+      s[30] = __fadd_rn(__fadd_rn(up[30], dn[30]), x[30]);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
+      for (int i = 2; i < 30; i += 2) {
         float t0, t1;
         fadd2(t0, t1, up[i], up[i + 1], dn[i], dn[i + 1]);
         fadd2(s[i], s[i + 1], t0, t1, x[i], x[i + 1]);
@@ -319,12 +325,12 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       e_rc0 = clock64();
 #endif
 
-      // One key row (32 accumulator columns = two TMEM loads) per iteration.
-      uint32_t a[16], c[16];
-      if (r_lo < r_hi) {
-        tc_ld16(taddr + r_lo * 32, a);
-        tc_ld16(taddr + r_lo * 32 + 16, c);
-      }
+      // One key row (32 accumulator columns = one TMEM load) per iteration.  Row addresses (TMEM row, group maxima and
+      // key norms of the row in shared memory) are running values behind an opaque copy: re-derived from the special
+      // registers in every iteration they were ~15 of the ~150 instructions of a row.
+      uint32_t xr[32];
+      const uint32_t trow0 = opaque_u32(taddr + (uint32_t)r_lo * 32u);
+      if (r_lo < r_hi) tc_ld32(trow0, xr);
       if (fresh && r_lo < r_hi) {
         // First tile of a list: one extra sweep over this group's rows finds their best score, and the entry bar
         // starts at (that - window) instead of -inf.  Without it the first rows push every key through the sorted
@@ -334,10 +340,9 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         for (int r = r_lo; r < r_hi; ++r) {
           tc_wait_ld();
           float s[32];
-          tap_sums(a, c, s);
+          tap_sums(xr, s);
           const int rn = r + 1 < r_hi ? r + 1 : r_lo;   // the last refill re-reads the first row for the main sweep
-          tc_ld16(taddr + rn * 32, a);
-          tc_ld16(taddr + rn * 32 + 16, c);
+          tc_ld32(taddr + rn * 32, xr);
           const float* rkr = rk_s + (r - r_lo) * 32;
           float vmax = -INFINITY;
 #pragma unroll
@@ -358,31 +363,30 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       tc_wait_ld();
       if (false)
 #endif
+      uint32_t trow = trow0;                                              // TMEM address of row r
+      uint32_t srow = opaque_u32(smem_u32(rk_s));                         // shared-memory address of row r's key norms
+      uint32_t sgm = srow + 128u * 4u;                                    // ... and of its four group maxima
 #pragma unroll 1
-      for (int r = r_lo; r < r_hi; ++r) {
+      for (int r = r_lo; r < r_hi; ++r, trow += 32u, srow += 32u * 4u, sgm += 4u * 4u) {
         tc_wait_ld();
 #ifdef SPEI_TCS_LDONLY   // timing experiment only: TMEM loads without any arithmetic
-        if (r + 1 < r_hi) { tc_ld16(taddr + (r + 1) * 32, a); tc_ld16(taddr + (r + 1) * 32 + 16, c); }
-        if (a[0] == 0x7fc12345u && c[3] == 0x7fc12345u) tv[0] = 1.f;
+        if (r + 1 < r_hi) tc_ld32(trow + 32u, xr);
+        if (xr[0] == 0x7fc12345u && xr[19] == 0x7fc12345u) tv[0] = 1.f;
         continue;
 #endif
         if (kDebug && p.debug_acc && pp == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            p.debug_acc[(size_t)m * kSAccCols + r * 32 + i] = __uint_as_float(a[i]);
-            p.debug_acc[(size_t)m * kSAccCols + r * 32 + 16 + i] = __uint_as_float(c[i]);
-          }
+          for (int i = 0; i < 32; ++i) p.debug_acc[(size_t)m * kSAccCols + r * 32 + i] = __uint_as_float(xr[i]);
         }
         float s[32];
-        tap_sums(a, c, s);
+        tap_sums(xr, s);
 #ifndef SPEI_TCS_NOLD      // (timing experiment: arithmetic without the TMEM reloads)
         if (r + 1 < r_hi)
 #else
         if (false)
 #endif
-        {  // a[], c[] are consumed: refill while the scores are examined
-          tc_ld16(taddr + (r + 1) * 32, a);
-          tc_ld16(taddr + (r + 1) * 32 + 16, c);
+        {  // xr[] is consumed: refill while the scores are examined
+          tc_ld32(trow + 32u, xr);
         }
         // Row test on the un-normalised tap sums: score[i] = s[i] * rk[i] <= max(s) * max(rk) when max(s) > 0 and
         // <= 0 otherwise (rk > 0), so a row whose bound does not beat the entry bar holds no candidate and its key
@@ -394,7 +398,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
           const float g1 = fmax3(fmax3(s[8], s[9], s[10]), fmax3(s[11], s[12], s[13]), fmaxf(s[14], s[15]));
           const float g2 = fmax3(fmax3(s[16], s[17], s[18]), fmax3(s[19], s[20], s[21]), fmaxf(s[22], s[23]));
           const float g3 = fmax3(fmax3(s[24], s[25], s[26]), fmax3(s[27], s[28], s[29]), s[30]);
-          const float4 gm = *reinterpret_cast<const float4*>(rk_s + 128 + (r - r_lo) * 4);   // broadcast read
+          const float4 gm = lds_f4(sgm);   // broadcast read
           // a non-positive maximum bounds its group's scores by 0; a NaN product (no key of the group inside the image)
           // fails every comparison and is dropped by fmaxf
           gb[0] = fmaxf(g0, 0.f) * gm.x; gb[1] = fmaxf(g1, 0.f) * gm.y; gb[2] = fmaxf(g2, 0.f) * gm.z; gb[3] = fmaxf(g3, 0.f) * gm.w;
@@ -416,7 +420,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (gb[g] > thr) {
-              const float4 ta = reinterpret_cast<const float4*>(rkr)[2 * g], tb = reinterpret_cast<const float4*>(rkr)[2 * g + 1];
+              const float4 ta = lds_f4(srow + 32u * g), tb = lds_f4(srow + 32u * g + 16u);
               const float rk8[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -518,6 +522,7 @@ int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   t.q_tu = p.q.tu; t.q_orient = p.q.orient; t.Uq = p.q.U; t.Vq = p.q.V; t.W = p.W; t.L = p.H * p.W;
   t.k_tu = p.k.tu; t.k_tvn = p.k.tv; t.k_tiles_img = p.k.tiles(); t.k_orient = p.k.orient; t.Ny = p.k.tile_v; t.Wr = p.Wr; t.lk1 = p.Hr * p.Wr;
   t.UkP = p.k.Upad; t.VkT = p.k.tv * p.k.tile_v;
+  if ((long long)p.n * p.rf * t.VkT * t.UkP >= (1ll << 31)) { set_error("relevance_tcs: key-norm array exceeds 32-bit offsets"); return SPEI_ERR_ARG; }
   const uint32_t ncols = (uint32_t)(kSBoxU * p.k.tile_v);
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bits 17-22, M>>4 at bits 24-28
   t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
