@@ -29,7 +29,8 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // Pick the orientation (and, for keys, the tile height Ny) that wastes the fewest padded positions.
 // dense:       tiles are 8 (u) x tile_v, MMA N = 8*Ny
 // tap-sharing: tiles are 30 interior (32 with halo) x tile_v, MMA N = 32*Ny; cost counts MMA columns
-static OperandPlan plan_operand(int H, int W, bool is_key, bool shared, int force_orient = -1, double* cost_out = nullptr) {
+static OperandPlan plan_operand(int H, int W, bool is_key, bool shared, int force_orient = -1, double* cost_out = nullptr,
+                                bool even_ny = false) {
   OperandPlan best{};
   double best_cost = 1e300;
   const int tile_u = shared ? kSTileU : kTileU, cols_u = shared ? kSBoxU : kTileU;
@@ -39,6 +40,7 @@ static OperandPlan plan_operand(int H, int W, bool is_key, bool shared, int forc
     const int U = orient == 0 ? W : H, V = orient == 0 ? H : W;
     const int ny_lo = is_key ? (shared ? 1 : 2) : qv, ny_hi = is_key ? max_ny : qv;
     for (int ny = ny_hi; ny >= ny_lo; ny -= (shared ? 1 : 2)) {
+      if (is_key && even_ny && (ny & 1)) continue;   // CTA pairs split the key rows of a tile between two CTAs
       OperandPlan o{};
       o.orient = orient; o.U = U; o.V = V; o.tile_u = tile_u; o.tile_v = ny;
       o.tu = ceil_div(U, tile_u); o.tv = ceil_div(V, ny);
@@ -64,6 +66,9 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   const bool shared = s.search == SPEI_SEARCH_TCS;
   p.mode = shared ? SPEI_SEARCH_TCS : SPEI_SEARCH_TC;
   p.nlist = shared ? tcs_epilogue_groups() : 1;
+  // tap-sharing kernel on CTA pairs (cta_group::2): two query tiles per step share every key tile
+  const bool pair = shared && tcs_cta_pairs() && num_sms >= 2;
+  p.pair = pair ? 1 : 0;
   p.n = s.n; p.rf = s.rf; p.H = s.h; p.W = s.w; p.Hr = s.hr; p.Wr = s.wr;
   p.io_bf16 = s.io_dtype == SPEI_IO_BF16;
   if (!shared) {
@@ -76,16 +81,18 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
     for (int orient = 0; orient < 2; ++orient) {
       double cq = 0, ck = 0;
       const OperandPlan oq = plan_operand(s.h, s.w, false, true, orient, &cq);
-      const OperandPlan ok = plan_operand(s.hr, s.wr, true, true, orient, &ck);
+      const OperandPlan ok = plan_operand(s.hr, s.wr, true, true, orient, &ck, pair);
       if (cq * ck < best - 1e-9) { best = cq * ck; p.q = oq; p.k = ok; }
     }
   }
   p.QT = p.q.tiles();
   p.KT = p.rf * p.k.tiles();
-  p.P = (long long)p.n * p.QT * p.KT;
-  p.G = (int)((p.P < (long long)num_sms) ? p.P : (long long)num_sms);
+  p.QTs = pair ? (p.QT + 1) / 2 : p.QT;
+  p.P = (long long)p.n * p.QTs * p.KT;
+  const int workers = pair ? num_sms / 2 : num_sms;   // persistent CTAs, or CTA pairs
+  p.G = (int)((p.P < (long long)workers) ? p.P : (long long)workers);
   p.maxseg = 1;
-  for (long long t = 0; t < (long long)p.n * p.QT; ++t) {
+  for (long long t = 0; t < (long long)p.n * p.QTs; ++t) {
     const long long p0 = t * p.KT;
     const int nseg = (int)(cta_of_pair(p0 + p.KT - 1, p.P, p.G) - cta_of_pair(p0, p.P, p.G)) + 1;
     if (nseg > p.maxseg) p.maxseg = nseg;
@@ -293,7 +300,7 @@ int spei_plan_info(const SpeiShape* shape, int32_t* out16) {
   Plan p;
   make_plan(*shape, sms, &p);
   const int32_t v[16] = {p.q.orient, p.q.tu, p.q.tv, p.q.Upad, p.q.Vpad, p.k.orient, p.k.tu, p.k.tv, p.k.tile_v, p.k.Upad, p.k.Vpad,
-                         p.QT, p.KT, p.G, p.maxseg, sms};
+                         p.QT, p.KT, p.G * (p.pair + 1), p.maxseg, sms};   // [13] = persistent CTAs (two per work range with CTA pairs)
   memcpy(out16, v, sizeof(v));
   return SPEI_OK;
 }

@@ -73,7 +73,8 @@ constexpr uint32_t kSTmemCols = 512;
 constexpr uint32_t kSAccCols = 256;
 
 struct TcsParams {
-  int n, rf, QT, KT, G, maxseg;
+  int n, rf, QT, KT, G, maxseg;   // QT = query work slots per item (tile pairs with kPair), G = workers (CTAs or CTA pairs)
+  int QTreal;                     // query tiles per item
   long long P;
   int q_tu, q_orient, Uq, Vq, W, L;
   int k_tu, k_tvn, k_tiles_img, k_orient, Ny, Wr, lk1, UkP, VkT;
@@ -105,7 +106,13 @@ __device__ __forceinline__ KeyTile key_tile_next(KeyTile t, int k_tu, int k_tvn,
   return t;
 }
 
-template <bool kDebug>
+// kPair: the kernel runs as clusters of two CTAs on one TPC (cta_group::2).  Rank 0 issues M = 256 MMAs for both: each CTA
+// holds its own query tile (128 accumulator rows in its own tensor memory) and HALF of the key rows of a stage, so a key tile
+// is fetched and read from shared memory once per TWO query tiles: per MMA an SM reads 4 KB of A + 4 KB of B instead of
+// 4 + 8 KB.  The barriers that gate the MMA issue (key stage full, query tile full, accumulator drained) live in rank 0's
+// shared memory: both producers' TMA loads count their bytes there and both CTAs' epilogue warps arrive there; every
+// tcgen05.commit is multicast to the barrier of the same name in both CTAs (stage free, query tile free, accumulator full).
+template <bool kDebug, bool kPair>
 __global__ void __launch_bounds__(kSThreads, 1)
 relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk, const TcsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -118,24 +125,31 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSQTileBytes + kSStages * kSStageBytesMax + kSNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;     // 0 = the CTA that issues the MMAs
+  const int b = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const long long pb = (long long)b * p.P / p.G, pe = (long long)(b + 1) * p.P / p.G;
   const long long cyc0 = clock64();   // CTA 0 publishes its clock64 span: the SM clock this kernel really ran at (bench.py)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kSStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_qfull, 1); mbar_init(bar_qfree, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4 * kSGroups); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4 * kSGroups * (kPair ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmq) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmk) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kSTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {   // one warp of EACH CTA of the pair, same shared-memory slot in both
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kSTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kSTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // register re-balancing (one warpgroup = 4 consecutive warps): the producer / issuer / allocator warps need few
@@ -150,29 +164,39 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       int qloaded = 0;
       PairIdx ix = decode_pair(pb, p.QT, p.KT);
       KeyTile kc = key_tile_decode(ix.kt, p.k_tiles_img, p.k_tu);
+      // kPair: each CTA loads its own query tile and its half of the key rows; the bytes of both are counted on rank 0's barrier
+      const uint32_t qfull_dst = kPair ? mapa_u32(bar_qfull, 0) : bar_qfull;
+      const int krow0 = kPair ? (int)rank * (p.Ny >> 1) : 0;
       for (long long pp = pb; pp < pe; ++pp, ix = next_pair(ix, p.QT, p.KT), kc = key_tile_next(kc, p.k_tu, p.k_tvn, p.rf)) {
         if (pp == pb || ix.kt == 0) {
           if (qloaded > 0) mbar_wait(bar_qfree, (uint32_t)((qloaded - 1) & 1), p.error_flag);
-          const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
-          mbar_arrive_expect_tx(bar_qfull, kSQTileBytes);
+          // (an odd tile count leaves rank 1 without a tile in the last pair: it re-reads the last one and drops the results)
+          const int qt = kPair ? min(2 * ix.qt + (int)rank, p.QTreal - 1) : ix.qt;
+          const int qtv = qt / p.q_tu, qtu = qt - qtv * p.q_tu;
+          if (rank == 0) mbar_arrive_expect_tx(bar_qfull, kSQTileBytes * (kPair ? 2u : 1u));
           // staged coordinates carry a 1-position border: interior position (u, v) lives at (u+1, v+1); the box
           // starts one position before the tile's first interior position in both directions
-          tma_load_4d(sQ, &tmq, bar_qfull, qtu * kSTileU * 8, qtv * kSQTileV, 0, ix.item);
+          if (kPair) tma_load_4d_pair(sQ, &tmq, qfull_dst, qtu * kSTileU * 8, qtv * kSQTileV, 0, ix.item);
+          else tma_load_4d(sQ, &tmq, bar_qfull, qtu * kSTileU * 8, qtv * kSQTileV, 0, ix.item);
           ++qloaded;
         }
         const int f = kc.f, ktv = kc.tv, ktu = kc.tu;
         for (uint32_t s4 = 0; s4 < kSStagesPerTile; ++s4) {
           mbar_wait_parked(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes);
-          tma_load_4d(sK + stage * kSStageBytesMax, &tmk, bar_full + 8 * stage, ktu * kSTileU * 8, ktv * p.Ny, (int)(s4 * kCGS),
-                      ix.item * p.rf + f);
+          if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, p.stage_bytes * (kPair ? 2u : 1u));
+          if (kPair)
+            tma_load_4d_pair(sK + stage * kSStageBytesMax, &tmk, mapa_u32(bar_full + 8 * stage, 0), ktu * kSTileU * 8, ktv * p.Ny + krow0,
+                             (int)(s4 * kCGS), ix.item * p.rf + f);
+          else
+            tma_load_4d(sK + stage * kSStageBytesMax, &tmk, bar_full + 8 * stage, ktu * kSTileU * 8, ktv * p.Ny, (int)(s4 * kCGS),
+                        ix.item * p.rf + f);
           if (++stage == kSStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       int qused = 0;
       uint32_t tile_i = 0;
@@ -204,14 +228,15 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
             for (uint32_t tap = 0; tap < 3; ++tap) {
               const uint64_t adesc = umma_desc_kmajor(qa + tap * kSRowBytes, kSQLBO, kSSBO);
               const uint64_t bdesc = umma_desc_kmajor(ka + tap * kSRowBytes, p.k_lbo, kSSBO);
-              tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (s4 | cgp | tap) != 0u);
+              if (kPair) tc_mma_bf16_pair(d_tmem, adesc, bdesc, p.idesc, (s4 | cgp | tap) != 0u);
+              else tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (s4 | cgp | tap) != 0u);
             }
           }
-          tc_commit(bar_empty + 8 * stage);
+          if (kPair) tc_commit_pair(bar_empty + 8 * stage); else tc_commit(bar_empty + 8 * stage);
           if (++stage == kSStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_tfull + 8 * acc);
-        if (ix.kt == p.KT - 1 && pp + 1 < pe) tc_commit(bar_qfree);
+        if (kPair) tc_commit_pair(bar_tfull + 8 * acc); else tc_commit(bar_tfull + 8 * acc);
+        if (ix.kt == p.KT - 1 && pp + 1 < pe) { if (kPair) tc_commit_pair(bar_qfree); else tc_commit(bar_qfree); }
       }
 #ifdef SPEI_TCS_PROF
       if (b == 3) printf("mma: total %lld wait_tempty %lld wait_full %lld tiles %lld\n", clock64() - pt0, p_tempty, p_full, pe - pb);
@@ -285,9 +310,11 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
       if (pp == pb || ix.kt == 0) {
 #pragma unroll
         for (int s = 0; s < kTopK; ++s) { tv[s] = -INFINITY; ti[s] = -1; }
-        const int qtv = ix.qt / p.q_tu, qtu = ix.qt - qtv * p.q_tu;
+        const int qt = kPair ? 2 * ix.qt + (int)rank : ix.qt;   // (kPair, odd tile count: the last pair's rank 1 has no tile)
+        const int qtv = qt / p.q_tu, qtu = qt - qtv * p.q_tu;
         const int u = qtu * kSTileU + qu - 1, v = qtv * kSQTileV + qv;
-        qlin = (qu >= 1 && qu <= kSTileU && u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W) : -1;
+        qlin = (qt < p.QTreal && qu >= 1 && qu <= kSTileU && u < p.Uq && v < p.Vq) ? (long long)ix.item * p.L + uv_to_linear(p.q_orient, u, v, p.W)
+                                                                                  : -1;
         winq = 0.f;
         if (qlin >= 0) {
           // fixed window (eps > 0) or the certified one (spei_common.cuh: certified_window)
@@ -374,7 +401,7 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
         if (xr[0] == 0x7fc12345u && xr[19] == 0x7fc12345u) tv[0] = 1.f;
         continue;
 #endif
-        if (kDebug && p.debug_acc && pp == 0) {
+        if (kDebug && p.debug_acc && pp == 0 && rank == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) p.debug_acc[(size_t)m * kSAccCols + r * 32 + i] = __uint_as_float(xr[i]);
         }
@@ -461,7 +488,10 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
 #endif
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_u32(bar_tempty + 8 * acc, 0));   // the issuing CTA's barrier counts both CTAs' warps
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       if (pp + 1 == pe || ix.kt == p.KT - 1) {
         if (qlin >= 0) {
           const long long p0 = ((long long)ix.item * p.QT + ix.qt) * p.KT;
@@ -484,11 +514,13 @@ relevance_tcs_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (b == 0 && threadIdx.x == 0) *reinterpret_cast<long long*>(p.error_flag + 2) = clock64() - cyc0;
+  if (kPair) cluster_sync_all();   // neither CTA leaves (or frees tensor memory) while its peer's MMAs / commits can still touch it
+  else __syncthreads();
+  if (b == 0 && rank == 0 && threadIdx.x == 0) *reinterpret_cast<long long*>(p.error_flag + 2) = clock64() - cyc0;
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kSTmemCols) : "memory");
   }
 }
 
@@ -508,25 +540,56 @@ static int make_map_s(EncodeTiledFn enc, CUtensorMap* tm, void* base, int nimg, 
 }
 
 int tcs_epilogue_groups() { return kSGroups; }
+// -DSPEI_TCS_PAIR=1 builds the kernel for CTA pairs.  Measured at 720p (round 2, parity suite green in both builds): 2.25 ms
+// against 2.21 ms on the same box -- a third fewer operand reads from shared memory and 40 % less key traffic from L2 do not
+// buy anything because neither bounds the kernel (the epilogue does), and the pair's two epilogues now have to finish
+// before either accumulator is free (max of two tile times instead of one).  Default: single CTAs.
+#ifndef SPEI_TCS_PAIR
+#define SPEI_TCS_PAIR 0
+#endif
+bool tcs_cta_pairs() { return SPEI_TCS_PAIR != 0; }
+
+template <bool kDebug, bool kPair>
+static int launch_tcs_t(const Plan& p, const CUtensorMap& tmq, const CUtensorMap& tmk, const TcsParams& t, cudaStream_t st) {
+  auto kern = relevance_tcs_kernel<kDebug, kPair>;
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes));
+  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.G * (kPair ? 2 : 1)));
+  cfg.blockDim = dim3(kSThreads);
+  cfg.dynamicSmemBytes = kSSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPEI_CUDA(cudaLaunchKernelEx(&cfg, kern, tmq, tmk, t));
+  SPEI_CUDA(cudaGetLastError());
+  return SPEI_OK;
+}
 
 int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
+  const bool pair = p.pair != 0;
+  if (pair && (p.k.tile_v & 1)) { set_error("relevance_tcs: CTA pairs need an even key tile height"); return SPEI_ERR_ARG; }
+  const int rows_cta = pair ? p.k.tile_v / 2 : p.k.tile_v;   // key rows of a tile one CTA stages
   CUtensorMap tmq, tmk;
   if ((rc = make_map_s(enc, &tmq, ws + p.off_qbf, p.n, p.q, kSQTileV + 2, kCG))) return rc;
-  if ((rc = make_map_s(enc, &tmk, ws + p.off_kbf, p.n * p.rf, p.k, p.k.tile_v + 2, kCGS))) return rc;
+  if ((rc = make_map_s(enc, &tmk, ws + p.off_kbf, p.n * p.rf, p.k, rows_cta + 2, kCGS))) return rc;
 
   TcsParams t{};
-  t.n = p.n; t.rf = p.rf; t.QT = p.QT; t.KT = p.KT; t.G = p.G; t.maxseg = p.maxseg; t.P = p.P;
+  t.n = p.n; t.rf = p.rf; t.QT = p.QTs; t.QTreal = p.QT; t.KT = p.KT; t.G = p.G; t.maxseg = p.maxseg; t.P = p.P;
   t.q_tu = p.q.tu; t.q_orient = p.q.orient; t.Uq = p.q.U; t.Vq = p.q.V; t.W = p.W; t.L = p.H * p.W;
   t.k_tu = p.k.tu; t.k_tvn = p.k.tv; t.k_tiles_img = p.k.tiles(); t.k_orient = p.k.orient; t.Ny = p.k.tile_v; t.Wr = p.Wr; t.lk1 = p.Hr * p.Wr;
   t.UkP = p.k.Upad; t.VkT = p.k.tv * p.k.tile_v;
   if ((long long)p.n * p.rf * t.VkT * t.UkP >= (1ll << 31)) { set_error("relevance_tcs: key-norm array exceeds 32-bit offsets"); return SPEI_ERR_ARG; }
   const uint32_t ncols = (uint32_t)(kSBoxU * p.k.tile_v);
-  // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bits 17-22, M>>4 at bits 24-28
-  t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
-  t.k_lbo = (uint32_t)(p.k.tile_v + 2) * kSRowBytes;
+  // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bits 17-22, M>>4 at bits 24-28 (M = 256 across a CTA pair)
+  t.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24);
+  t.k_lbo = (uint32_t)(rows_cta + 2) * kSRowBytes;
   t.stage_bytes = kCGS * t.k_lbo;
   t.win = eps > 0.f ? eps * 1.02f : 0.f;   // <= 0: certified per-query window
   t.rq = (const float*)(ws + p.off_rq);
@@ -538,12 +601,10 @@ int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st) {
   t.debug_acc = take_debug_acc();
   t.error_flag = (int*)(ws + p.off_errflag);
   SPEI_CUDA(cudaMemsetAsync(t.error_flag, 0, sizeof(int), st));
-  auto kern = t.debug_acc ? relevance_tcs_kernel<true> : relevance_tcs_kernel<false>;
-  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes));
-  SPEI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-  kern<<<p.G, kSThreads, kSSmemBytes, st>>>(tmq, tmk, t);
-  SPEI_CUDA(cudaGetLastError());
-  return SPEI_OK;
+#if SPEI_TCS_PAIR
+  if (pair) return t.debug_acc ? launch_tcs_t<true, true>(p, tmq, tmk, t, st) : launch_tcs_t<false, true>(p, tmq, tmk, t, st);
+#endif
+  return t.debug_acc ? launch_tcs_t<true, false>(p, tmq, tmk, t, st) : launch_tcs_t<false, false>(p, tmq, tmk, t, st);
 }
 
 }  // namespace spei

@@ -30,7 +30,7 @@ __host__ __device__ inline long long cta_of_pair_d(long long p, long long P, int
 struct RescoreParams {
   int n, rf, H, W, Hr, Wr;
   int q_orient, q_tu, q_tile_u, q_tile_v, nlist;  // query tile grid (to find a query's tile -> its segment count)
-  int QT, KT, G, maxseg;
+  int QT, pair, KT, G, maxseg;
   long long P;
   float eps;                  // > 0: fixed window; <= 0: certified
   const float *q32, *k32, *rq, *rk, *qss, *dq;
@@ -82,7 +82,7 @@ rescore_kernel(const RescoreParams p) {
   // which query tile is this, and into how many key segments was it split?
   const int u = p.q_orient == 0 ? x : y, v = p.q_orient == 0 ? y : x;
   const int qt = (v / p.q_tile_v) * p.q_tu + (u / p.q_tile_u);
-  const long long p0 = ((long long)n * p.QT + qt) * p.KT;
+  const long long p0 = ((long long)n * p.QT + (qt >> p.pair)) * p.KT;   // (QT = work slots per item: tile pairs with cta_group::2)
   const int nseg = (int)(cta_of_pair_d(p0 + p.KT - 1, p.P, p.G) - cta_of_pair_d(p0, p.P, p.G)) + 1;
   const int nlists = nseg * p.nlist;  // lists of a query are contiguous: [segment][list][kTopK]
   const int ncand = nlists * kTopK;
@@ -382,7 +382,7 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   if (rc) return rc;
   RescoreParams r{};
   r.n = p.n; r.rf = p.rf; r.H = p.H; r.W = p.W; r.Hr = p.Hr; r.Wr = p.Wr;
-  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.QT = p.QT; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
+  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.QT = p.QTs; r.pair = p.pair; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
   r.eps = eps;
   r.q32 = (const float*)(ws + p.off_q32); r.k32 = (const float*)(ws + p.off_k32);
   r.rq = (const float*)(ws + p.off_rq); r.rk = (const float*)(ws + p.off_rk); r.qss = (const float*)(ws + p.off_qss);

@@ -61,9 +61,11 @@ struct Plan {
   int H, W, Hr, Wr;
   OperandPlan q, k;
   int QT;          // query tiles per item
+  int pair;        // 1: the tap-sharing kernel runs on CTA pairs (cta_group::2), one work step = two query tiles x one key tile
+  int QTs;         // query work slots per item: QT, or ceil(QT / 2) with CTA pairs
   int KT;          // key tiles per item (all reference frames)
-  long long P;     // total (query tile, key tile) pairs = n*QT*KT
-  int G;           // persistent CTAs
+  long long P;     // total work steps = n*QTs*KT
+  int G;           // persistent CTAs (CTA pairs when pair = 1)
   int maxseg;      // max key segments a query tile is split into
   // workspace offsets (bytes)
   size_t off_qbf, off_kbf, off_q32, off_k32, off_rq, off_rk, off_rkpad, off_qss, off_kss;
@@ -92,6 +94,7 @@ int launch_stage_norm(const Plan& p, const void* q, const void* k, char* ws, cud
 int launch_relevance_tc(const Plan& p, float eps, char* ws, cudaStream_t st);
 int launch_relevance_tcs(const Plan& p, float eps, char* ws, cudaStream_t st);
 int tcs_epilogue_groups();   // candidate lists per (query, key segment) the tap-sharing kernel writes
+bool tcs_cta_pairs();        // the tap-sharing kernel was built for CTA pairs (cta_group::2)
 void set_debug_acc(float* ptr);
 int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws,
                    cudaStream_t st);
