@@ -19,7 +19,8 @@
 // ladder at 720p: MMA + TMA only 1.69 ms; + TMEM loads 1.71; + tap-sum adds, maxima, bookkeeping 1.85; + the 60 lane
 // shuffles per key row 2.08; + the insertion path 2.27 (kTopK 16, one bound per row) -> 2.15 ms with kTopK 8 and the
 // per-group row test below.  More epilogue warps are slower, the query operand from tensor memory is slower (2.71 ms),
-// tcgen05.shift / lane-offset tcgen05.ld cannot replace the shuffles (tools/exp/).  The chip also runs the kernel at its
+// tcgen05.shift / lane-offset tcgen05.ld cannot replace the shuffles (tools/exp/); a scheduler issues one SHFL per 3-4 cycles
+// (tools/exp/exp_shfl.cu), so the exchange alone is ~1 600 of a tile's 3 072 MMA cycles.  The chip also runs the kernel at its
 // power cap (sw_power_cap, 1.67-1.75 GHz); tensor pipe 62 % active.
 //
 // Operand layout: the same channel-group-planar bf16 images as the dense kernel ([16][Vpad][Upad][8],
