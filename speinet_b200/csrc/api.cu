@@ -133,6 +133,8 @@ int make_plan(const SpeiShape& s, int num_sms, Plan* out) {
   p.off_errflag = take(64);
   p.off_ref3n = take(nk * Lk1 * kC3 * 4);        // channels-last copies of ref_lv3 (when it is not the searched tensor)
   p.off_ref2n = take(nk * Lk1 * 4 * (kC3 / 2) * 4);  // ... and of ref_lv2 ([2hr][2wr][64])
+  p.off_ref1c = take(nk * Lk1 * 16 * (size_t)s.c1 * 4);   // cell-major copy of ref_lv1 ([c1][hr][wr][4 x 4])
+  p.off_gmode = take(64);                                 // lv1 gather: path chosen from the match field (gather_fold.cu)
   p.total = off;
   *out = p;
   return SPEI_OK;
@@ -314,7 +316,7 @@ static int gather_level(const Plan& p, const SpeiShape* shape, int level, const 
   const int c = level == 3 ? shape->c3 : (level == 2 ? shape->c2 : shape->c1);
   if (level == 1)
     return launch_gather_fold(shape->n, shape->rf, c, shape->h, shape->w, shape->hr, shape->wr, scale, shape->fold_mode, arg32, ref,
-                              out, p.io_bf16, st);
+                              ws + p.off_ref1c, (int*)(ws + p.off_gmode), out, p.io_bf16, st);
   const float* src;
   if (level == 3 && staged_k != nullptr && ref == staged_k) {
     src = (const float*)(ws + p.off_k32);

@@ -71,7 +71,7 @@ struct Plan {
   size_t off_qbf, off_kbf, off_q32, off_k32, off_rq, off_rk, off_rkpad, off_qss, off_kss;
   size_t off_qrs, off_krs;     // per-pixel energy of the bf16 rounding residual  sum_c (x - bf16(x))^2
   size_t off_dq, off_dkmax;    // per-query relative residual norm of its patch; per-item maximum over the keys (float bits)
-  size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag, off_ref3n, off_ref2n;
+  size_t off_cval, off_cidx, off_flag, off_packed, off_counters, off_arg32, off_errflag, off_ref3n, off_ref2n, off_ref1c, off_gmode;
   // second pass (relevance_flagged.cu): packed A operand, per-row threshold / query id, emitted pairs
   size_t off_thr, off_apack, off_prow_thr, off_prow_q, off_emit_q, off_emit_k;
   int flag_rows;               // capacity of the packed A operand in query rows (multiple of 128)
@@ -113,8 +113,8 @@ __host__ __device__ inline float certified_delta(float dq, float dkmax) {
 constexpr float kWindowMargin = 1.0e-3f;
 __host__ __device__ inline float certified_window(float delta) { return delta + kWindowMargin; }
 int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st);
-int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
-                       const int32_t* arg32, const void* ref, void* out, int io_bf16, cudaStream_t st);
+int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
+                       const void* ref, void* ref_cells, int* mode, void* out, int io_bf16, cudaStream_t st);
 int launch_stage_ref_nhwc(const void* ref, int in_bf16, int nimg, int C, int Hs, int Ws, float* dst, cudaStream_t st);
 int launch_gather_fold_nhwc(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode,
                             const int32_t* arg32, const float* ref_nhwc, void* out, int out_bf16, cudaStream_t st);

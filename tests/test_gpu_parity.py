@@ -182,6 +182,29 @@ def test_gather_fold_multi_frame_and_oracle_closed_form(dims):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("field", ["identity", "jitter2", "random"])
+@pytest.mark.parametrize("dims", [(1, 45, 80, 45, 80, 1), (2, 9, 37, 11, 41, 2)])
+def test_gather_fold_lv1_both_source_layouts(field, dims):
+    """The finest level picks its source layout from the match field on the device (planar input on a coherent field, the
+    re-tiled cell-major copy on a scattered one; gather_fold.cu): both must give the oracle's closed form bit for bit."""
+    rng = np.random.default_rng(11)
+    n, h, w, hr, wr, rf = dims
+    yy, xx = np.divmod(np.arange(h * w), w)
+    if field == "random":
+        arg = rng.integers(0, rf * hr * wr, size=(n, h * w))
+    else:
+        m = 0 if field == "identity" else 2
+        cy = np.clip(yy[None] + rng.integers(-m, m + 1, size=(n, h * w)), 0, hr - 1)
+        cx = np.clip(xx[None] + rng.integers(-m, m + 1, size=(n, h * w)), 0, wr - 1)
+        arg = rng.integers(0, rf, size=(n, 1)) * hr * wr + cy * wr + cx
+    arg = arg.astype(np.int32)
+    refs = [rng.standard_normal((n, 32, 4 * hr, 4 * wr)).astype(np.float32) for _ in range(rf)]
+    want = oracle.closed_form_transfer(arg, refs, 4, h, w, fold_order="cuda", div_mode="cuda")
+    ref = torch.stack([cu(r) for r in refs], dim=1).contiguous()
+    got = U.gather_fold(cu(arg), ref, 1, n, h, w, hr, wr, rf, _lib.FOLD_CUDA)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 # ------------------------------------------------------------------ whole module ---------------
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_module_matches_reference_golden(golden, name):

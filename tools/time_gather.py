@@ -29,11 +29,16 @@ for name, arg in fields.items():
         fn = lambda: _lib.check(lib.spei_gather_fold(ctypes.byref(shape), lvl, U.vp(arg), U.vp(ref), U.vp(out), ctypes.c_void_p(0),
                                                      ctypes.c_void_p(wsp), nbytes, st), "gf")
         for _ in range(2): fn()
-        ts = []
-        for _ in range(7):
-            flush.zero_()   # cold L2
+        # cold L2 per call, host launch latency hidden: 10 x (flush + call) against 10 x flush, each in one timed region
+        def region(with_fn):
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
-        res[f"{name}_lv{lvl}_us"] = round(sorted(ts)[3], 1)
+            e0.record()
+            for _ in range(10):
+                flush.zero_()
+                if with_fn: fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 100.0   # us per iteration
+        ts = sorted(region(True) - region(False) for _ in range(3))
+        res[f"{name}_lv{lvl}_us"] = round(ts[1], 1)
 print(json.dumps(res))
