@@ -45,7 +45,7 @@ CONFIG = {"workload": WORKLOAD, "query_grid": [H, W], "ref_grid": [H, W], "ref_f
 # kernels of this repo launched per step (one clip): see DESIGN.md section 4
 KERNELS_PER_STEP = {"stage (zero_padding, stage_transpose, patch_norms)": 3, "search (relevance_tcs)": 1,
                     "exactness (clear, rescore, flagged pack / tcgen05 emission / rescoring, exhaustive fallback, unpack)": 7,
-                    "gather_fold lv3/lv2/lv1 (+ the channels-last copy of ref_lv2)": 4, "fuse_level lv3/lv2/lv1": 3}
+                    "gather_fold lv3/lv2/lv1 (+ the channels-last copy of ref_lv2, + the match-field probe / cell-major copy of ref_lv1)": 5, "fuse_level lv3/lv2/lv1": 3}
 
 
 def peaks():
