@@ -182,15 +182,30 @@ gather_fold_lv1_kernel(const int32_t* __restrict__ arg, const TIO* __restrict__ 
   const unsigned in_step = cells ? (unsigned)plane : (unsigned)ref_pitch;   // next channel / next pixel row of the source
   const TIO* base[9];
   unsigned step[9];
+  bool same = true;   // all nine neighbours point at the same source cell (a locally rigid match field: the usual case on video)
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int o = s_src[t][cell];
     base[t] = o >= 0 ? rbase + o : reinterpret_cast<const TIO*>(&g_zero16);   // 16 zero bytes: zero in either type
     step[t] = o >= 0 ? in_step : 0u;                                          // (stride 0 for the zero constant)
+    same = same && o >= 0 && o == s_src[0][cell];
   }
   const size_t out_plane = (size_t)(S * H) * (S * W);
   TIO* obase = out + ((size_t)n * C + c) * out_plane + (size_t)(Y * S + r) * (S * W) + (size_t)X * S;
   const size_t out_step = cells ? out_plane : (size_t)(S * W);
+  if (same) {   // one request instead of nine; the value is added nine times in the same order: identical sum
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = load_run4(base[0] + (size_t)i * step[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) vadd(acc, v[i]);
+      store_run4(obase + (size_t)i * out_step, fin<kTrueDiv>(acc));
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float4 v[9];

@@ -110,7 +110,10 @@ __host__ __device__ inline float certified_delta(float dq, float dkmax) {
 // b - (Delta + margin), which covers that set whenever E >= b - margin.  A query whose best candidate's bf16 score is off by
 // more than the margin (rigorously possible up to Delta, measured <= 6e-4) is queued for the second pass like a saturated one,
 // so the result stays certified while the common case pays for a 1.6x narrower window than the worst-case 2 * Delta.
-constexpr float kWindowMargin = 1.0e-3f;
+#ifndef SPEI_WINDOW_MARGIN
+#define SPEI_WINDOW_MARGIN 1.0e-3f
+#endif
+constexpr float kWindowMargin = SPEI_WINDOW_MARGIN;
 __host__ __device__ inline float certified_window(float delta) { return delta + kWindowMargin; }
 int launch_exact_all(const Plan& p, float* S, int32_t* arg32, int64_t* arg64, int32_t* stats, char* ws, cudaStream_t st);
 int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int scale, int fold_mode, const int32_t* arg32,
