@@ -34,12 +34,20 @@ __device__ __forceinline__ float exact_relevance(QTap qtap, const float* __restr
   // row and is zeroed); the kernel is latency bound, so loads in flight are what matters
   const float4* kc = reinterpret_cast<const float4*>(kimg) + ((size_t)hr * Wr + wr) * (kC3 / 4) + lane;
   float4 kv[9];
+  if ((unsigned)(hr - 1) < (unsigned)(Hr - 2) && (unsigned)(wr - 1) < (unsigned)(Wr - 2)) {
+    // interior key (the whole warp works on the same key: uniform branch): nine plain loads, no bounds logic
+    const int rowq = Wr * (kC3 / 4);
+    const float4* k0 = kc - rowq - (kC3 / 4);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int dy = t / 3 - 1, dx = t % 3 - 1;
-    const bool in = (unsigned)(hr + dy) < (unsigned)Hr && (unsigned)(wr + dx) < (unsigned)Wr;
-    kv[t] = __ldg(kc + (in ? (dy * Wr + dx) * (kC3 / 4) : 0));
-    if (!in) kv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < 9; ++t) kv[t] = __ldg(k0 + (t / 3) * rowq + (t % 3) * (kC3 / 4));
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const bool in = (unsigned)(hr + dy) < (unsigned)Hr && (unsigned)(wr + dx) < (unsigned)Wr;
+      kv[t] = __ldg(kc + (in ? (dy * Wr + dx) * (kC3 / 4) : 0));
+      if (!in) kv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // three independent chains (taps t % 3), fixed order
 #pragma unroll

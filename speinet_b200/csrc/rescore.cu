@@ -32,6 +32,7 @@ struct RescoreParams {
   int q_orient, q_tu, q_tile_u, q_tile_v, nlist;  // query tile grid (to find a query's tile -> its segment count)
   int QT, pair, KT, G, maxseg;
   long long P;
+  FastDiv div_lk1, div_wr;    // key index -> (frame, row, column)
   float eps;                  // > 0: fixed window; <= 0: certified
   const float *q32, *k32, *rq, *rk, *qss, *dq;
   const int* dkmax;
@@ -126,7 +127,7 @@ rescore_kernel(const RescoreParams p) {
     return reinterpret_cast<const float4*>(&qrows[(wy + t / 3) * kRBH + wx + t % 3][0]);
   };
   auto exact = [&](int jj) {
-    const int f = jj / lk1, rem = jj - f * lk1, hr = rem / p.Wr, wr = rem - hr * p.Wr;
+    const int f = p.rf == 1 ? 0 : fast_div(jj, p.div_lk1), rem = jj - f * lk1, hr = fast_div(rem, p.div_wr), wr = rem - hr * p.Wr;
     const float rk = __ldg(p.rk + ((size_t)n * p.rf + f) * lk1 + rem);
     return exact_relevance(qtap, p.k32 + ((size_t)n * p.rf + f) * lk1 * kC3, hr, wr, p.Hr, p.Wr, rq, rk, lane);
   };
@@ -382,7 +383,7 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   if (rc) return rc;
   RescoreParams r{};
   r.n = p.n; r.rf = p.rf; r.H = p.H; r.W = p.W; r.Hr = p.Hr; r.Wr = p.Wr;
-  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.QT = p.QTs; r.pair = p.pair; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
+  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.div_lk1 = make_fastdiv(p.Hr * p.Wr); r.div_wr = make_fastdiv(p.Wr); r.QT = p.QTs; r.pair = p.pair; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
   r.eps = eps;
   r.q32 = (const float*)(ws + p.off_q32); r.k32 = (const float*)(ws + p.off_k32);
   r.rq = (const float*)(ws + p.off_rq); r.rk = (const float*)(ws + p.off_rk); r.qss = (const float*)(ws + p.off_qss);
