@@ -27,12 +27,19 @@ __host__ __device__ inline long long cta_of_pair_d(long long p, long long P, int
   return ((p + 1) * (long long)G - 1) / P;
 }
 
+// the same with the division by P as one multiply-high (FastDiv, spei_common.cuh) when (P + 1) * G stays below 2^31
+__device__ __forceinline__ long long cta_of_pair_f(long long p, long long P, int G, const FastDiv divP) {
+  if ((P + 1) * (long long)G < (1ll << 31)) return (long long)fast_div((int)(p + 1) * G - 1, divP);
+  return cta_of_pair_d(p, P, G);
+}
+
 struct RescoreParams {
   int n, rf, H, W, Hr, Wr;
   int q_orient, q_tu, q_tile_u, q_tile_v, nlist;  // query tile grid (to find a query's tile -> its segment count)
   int QT, pair, KT, G, maxseg;
   long long P;
   FastDiv div_lk1, div_wr;    // key index -> (frame, row, column)
+  FastDiv div_tu, div_tv, div_P;   // query position -> tile; work step -> persistent CTA
   float eps;                  // > 0: fixed window; <= 0: certified
   const float *q32, *k32, *rq, *rk, *qss, *dq;
   const int* dkmax;
@@ -82,9 +89,9 @@ rescore_kernel(const RescoreParams p) {
 
   // which query tile is this, and into how many key segments was it split?
   const int u = p.q_orient == 0 ? x : y, v = p.q_orient == 0 ? y : x;
-  const int qt = (v / p.q_tile_v) * p.q_tu + (u / p.q_tile_u);
+  const int qt = fast_div(v, p.div_tv) * p.q_tu + fast_div(u, p.div_tu);
   const long long p0 = ((long long)n * p.QT + (qt >> p.pair)) * p.KT;   // (QT = work slots per item: tile pairs with cta_group::2)
-  const int nseg = (int)(cta_of_pair_d(p0 + p.KT - 1, p.P, p.G) - cta_of_pair_d(p0, p.P, p.G)) + 1;
+  const int nseg = (int)(cta_of_pair_f(p0 + p.KT - 1, p.P, p.G, p.div_P) - cta_of_pair_f(p0, p.P, p.G, p.div_P)) + 1;
   const int nlists = nseg * p.nlist;  // lists of a query are contiguous: [segment][list][kTopK]
   const int ncand = nlists * kTopK;
   const float* cv = p.cval + (size_t)wq * p.maxseg * p.nlist * kTopK;
@@ -383,7 +390,8 @@ int launch_rescore(const Plan& p, float eps, float* S, int32_t* arg32, int64_t* 
   if (rc) return rc;
   RescoreParams r{};
   r.n = p.n; r.rf = p.rf; r.H = p.H; r.W = p.W; r.Hr = p.Hr; r.Wr = p.Wr;
-  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.div_lk1 = make_fastdiv(p.Hr * p.Wr); r.div_wr = make_fastdiv(p.Wr); r.QT = p.QTs; r.pair = p.pair; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
+  r.q_orient = p.q.orient; r.q_tu = p.q.tu; r.q_tile_u = p.q.tile_u; r.q_tile_v = p.q.tile_v; r.nlist = p.nlist; r.div_lk1 = make_fastdiv(p.Hr * p.Wr); r.div_wr = make_fastdiv(p.Wr);
+  r.div_tu = make_fastdiv(p.q.tile_u); r.div_tv = make_fastdiv(p.q.tile_v); r.div_P = make_fastdiv((int)(p.P < (1ll << 31) ? p.P : 1)); r.QT = p.QTs; r.pair = p.pair; r.KT = p.KT; r.G = p.G; r.maxseg = p.maxseg; r.P = p.P;
   r.eps = eps;
   r.q32 = (const float*)(ws + p.off_q32); r.k32 = (const float*)(ws + p.off_k32);
   r.rq = (const float*)(ws + p.off_rq); r.rk = (const float*)(ws + p.off_rk); r.qss = (const float*)(ws + p.off_qss);
