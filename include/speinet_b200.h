@@ -40,6 +40,10 @@ extern "C" {
 #define SPEI_FOLD_TRUE_DIV 2  /* bit 1: true division by 9 instead of x * (1.0f/9.0f)          */
 #define SPEI_FOLD_CUDA 0      /* what torch does on a CUDA device: CUDA col2im order, x*(1/9f) */
 #define SPEI_FOLD_CPU 3       /* what torch does on the CPU: CPU col2im order, x/9             */
+/* Finest level (lv1) of spei_gather_fold: source layout.  Default (neither bit): chosen on the device from the match field
+ * (planar input when coherent or when the level is small, a cell-major copy when scattered); results are identical. */
+#define SPEI_FOLD_LV1_PLANAR 4 /* bit 2: always gather from the caller's planar tensor           */
+#define SPEI_FOLD_LV1_CELLS 8  /* bit 3: always re-tile ref_lv1 cell-major first                 */
 
 /* element type of the feature tensors that cross the boundary */
 #define SPEI_IO_F32 0

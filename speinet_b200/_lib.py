@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("SPEINET_B200_LIB") or os.path.join(_PKG, "libspeinet_
 
 FOLD_CUDA, FOLD_CPU = 0, 3
 FOLD_ORDER_CPU, FOLD_TRUE_DIV = 1, 2
+FOLD_LV1_PLANAR, FOLD_LV1_CELLS = 4, 8   # pin the source layout of the finest gather level (default: chosen on the device)
 SEARCH_TC, SEARCH_EXACT, SEARCH_TCS = 0, 1, 2
 IO_F32, IO_BF16 = 0, 1
 STATS_WORDS = 8   # SPEI_STATS_WORDS

@@ -167,7 +167,7 @@ static int check_shape(const SpeiShape* s) {
   if ((long long)s->rf * s->hr * s->wr >= (1ll << 31) || (long long)s->n * s->h * s->w >= (1ll << 31)) {
     set_error("index space exceeds int32"); return SPEI_ERR_ARG;
   }
-  if (s->fold_mode < 0 || s->fold_mode > 3) { set_error("bad fold_mode %d", s->fold_mode); return SPEI_ERR_ARG; }
+  if (s->fold_mode < 0 || s->fold_mode > 15 || (s->fold_mode & 12) == 12) { set_error("bad fold_mode %d", s->fold_mode); return SPEI_ERR_ARG; }
   if (s->io_dtype != SPEI_IO_F32 && s->io_dtype != SPEI_IO_BF16) { set_error("bad io_dtype %d", s->io_dtype); return SPEI_ERR_ARG; }
   if (s->search != SPEI_SEARCH_TC && s->search != SPEI_SEARCH_EXACT && s->search != SPEI_SEARCH_TCS) {
     set_error("bad search %d", s->search); return SPEI_ERR_ARG;

@@ -147,7 +147,7 @@ gather_fold_lv1_kernel(const int32_t* __restrict__ arg, const TIO* __restrict__ 
                        int rf, int C, int H, int W, int Hr, int Wr, const int* __restrict__ mode) {
   constexpr int S = 4;
   __shared__ int s_src[9][32];   // per (neighbour, cell): element offset of the source run inside the item's reference, -1 = none
-  const bool cells = __ldg(mode) != 0;
+  const bool cells = mode != nullptr && __ldg(mode) != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int X0 = blockIdx.x * 32, Y = blockIdx.y;
   const int slabs = C / 8, n = blockIdx.z / slabs, slab0 = (blockIdx.z - n * slabs) * 8;
@@ -229,13 +229,16 @@ int launch_gather_fold(int n, int rf, int c, int h, int w, int hr, int wr, int s
   if ((long long)n * (c / 8) > 65535 || h > 65535) { set_error("gather_fold: grid too large (n * c / 8 = %lld)", (long long)n * (c / 8)); return SPEI_ERR_ARG; }
   if ((long long)rf * c * hr * wr >= (1ll << 31) / 16 || (long long)n * h * w >= (1ll << 31)) { set_error("gather_fold: level exceeds 32-bit offsets"); return SPEI_ERR_ARG; }
   const bool cpu_order = (fold_mode & SPEI_FOLD_ORDER_CPU) != 0, true_div = (fold_mode & SPEI_FOLD_TRUE_DIV) != 0;
-  const int force = SPEI_GATHER_LV1 == 0 ? -1 : SPEI_GATHER_LV1 - 1;
+  const int force = (fold_mode & SPEI_FOLD_LV1_PLANAR) ? 0 : ((fold_mode & SPEI_FOLD_LV1_CELLS) ? 1 : (SPEI_GATHER_LV1 == 0 ? -1 : SPEI_GATHER_LV1 - 1));
   int sms = 0, dev = 0;
   SPEI_CUDA(cudaGetDevice(&dev));
   SPEI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long items = (long long)n * rf * c * hr * ((wr + 63) / 64);
   const int rgrid = (int)(items < (long long)sms * 8 ? items : (long long)sms * 8);
-  if (io_bf16)
+  // a level that fits L2 several times over (<= 32 MB: 256 x 256 clips, BSD crops) never pays for sector waste: planar, one launch
+  const bool small = (long long)n * rf * c * hr * wr * 16 * (io_bf16 ? 2 : 4) <= (32ll << 20);
+  if (force == 0 || (small && force < 0)) mode = nullptr;
+  else if (io_bf16)
     stage_ref_cell_kernel<<<rgrid, 256, 0, st>>>((const __nv_bfloat16*)ref, n * rf * c, hr, wr, (__nv_bfloat16*)ref_cells, arg32, n, rf, h, w, mode, force);
   else
     stage_ref_cell_kernel<<<rgrid, 256, 0, st>>>((const float*)ref, n * rf * c, hr, wr, (float*)ref_cells, arg32, n, rf, h, w, mode, force);

@@ -182,11 +182,13 @@ def test_gather_fold_multi_frame_and_oracle_closed_form(dims):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("layout", ["auto", "planar", "cells"])
 @pytest.mark.parametrize("field", ["identity", "jitter2", "random"])
 @pytest.mark.parametrize("dims", [(1, 45, 80, 45, 80, 1), (2, 9, 37, 11, 41, 2)])
-def test_gather_fold_lv1_both_source_layouts(field, dims):
-    """The finest level picks its source layout from the match field on the device (planar input on a coherent field, the
-    re-tiled cell-major copy on a scattered one; gather_fold.cu): both must give the oracle's closed form bit for bit."""
+def test_gather_fold_lv1_both_source_layouts(field, dims, layout):
+    """The finest level gathers from the planar input or from a re-tiled cell-major copy (gather_fold.cu; chosen on the device
+    from the match field for large levels, pinned here through the SPEI_FOLD_LV1_* bits): every combination must give the
+    oracle's closed form bit for bit."""
     rng = np.random.default_rng(11)
     n, h, w, hr, wr, rf = dims
     yy, xx = np.divmod(np.arange(h * w), w)
@@ -201,7 +203,8 @@ def test_gather_fold_lv1_both_source_layouts(field, dims):
     refs = [rng.standard_normal((n, 32, 4 * hr, 4 * wr)).astype(np.float32) for _ in range(rf)]
     want = oracle.closed_form_transfer(arg, refs, 4, h, w, fold_order="cuda", div_mode="cuda")
     ref = torch.stack([cu(r) for r in refs], dim=1).contiguous()
-    got = U.gather_fold(cu(arg), ref, 1, n, h, w, hr, wr, rf, _lib.FOLD_CUDA)
+    mode = _lib.FOLD_CUDA | {"auto": 0, "planar": _lib.FOLD_LV1_PLANAR, "cells": _lib.FOLD_LV1_CELLS}[layout]
+    got = U.gather_fold(cu(arg), ref, 1, n, h, w, hr, wr, rf, mode)
     assert np.array_equal(got.cpu().numpy(), want)
 
 
