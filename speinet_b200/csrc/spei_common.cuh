@@ -8,6 +8,8 @@
 
 #include "../../include/speinet_b200.h"
 
+#include "fastdiv.h"
+
 namespace spei {
 
 // ---- fixed geometry of the search -------------------------------------------------------------
@@ -135,26 +137,6 @@ int launch_rl_deconv(int n, int c, int h, int w, int ks, int iters, float lambda
 
 int launch_conv1x1(int n, int cin, int cout, long long P, const float* x, const float* w, float* y, cudaStream_t st);
 int launch_upsample2_bias_act(int n, int c, int h, int w, const float* y, const float* bias, int relu, float* out, cudaStream_t st);
-
-// Division of a non-negative int (< 2^31) by a launch-invariant positive divisor with one multiply-high and one shift
-// (exact: m = ceil(2^k / d), k = 31 + ceil(log2 d), error term n * (m d - 2^k) < 2^k for n < 2^31).  The compiler's generic
-// 32-bit division is ~20 instructions; the rescoring kernels decode two key indices per exact score.
-struct FastDiv {
-  unsigned m, sh;
-  int d;
-};
-inline FastDiv make_fastdiv(int d) {
-  FastDiv f{0u, 0u, d};
-  if (d > 1) {
-    int lg = 0;
-    while ((1ll << lg) < (long long)d) ++lg;              // ceil(log2 d)
-    const int k = 31 + lg;
-    f.m = (unsigned)(((1ull << k) + (unsigned long long)d - 1) / (unsigned long long)d);
-    f.sh = (unsigned)(k - 32);
-  }
-  return f;
-}
-__device__ __forceinline__ int fast_div(int n, const FastDiv f) { return f.d == 1 ? n : (int)(__umulhi((unsigned)n, f.m) >> f.sh); }
 
 // position <-> index helpers shared by kernels
 __host__ __device__ inline int uv_to_linear(int orient, int u, int v, int W) {

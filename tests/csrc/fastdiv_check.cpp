@@ -1,12 +1,6 @@
 #include <cstdio>
 #include <cstdint>
-struct FastDiv { unsigned m, sh; int d; };
-inline FastDiv make_fastdiv(int d) {
-  FastDiv f{0u, 0u, d};
-  if (d > 1) { int lg = 0; while ((1ll << lg) < (long long)d) ++lg; const int k = 31 + lg;
-    f.m = (unsigned)(((1ull << k) + (unsigned long long)d - 1) / (unsigned long long)d); f.sh = (unsigned)(k - 32); }
-  return f; }
-static int fast_div(int n, FastDiv f) { return f.d == 1 ? n : (int)((((unsigned long long)(unsigned)n * f.m) >> 32) >> f.sh); }
+#include "../../speinet_b200/csrc/fastdiv.h"
 int main() {
   long long bad = 0;
   int ds[] = {1,2,3,5,7,8,9,17,40,45,80,320,321,57600,57601,65536,100003,1<<20,(1<<30)+1,2147483647};

@@ -219,3 +219,18 @@ def test_forward_sync_free_equals_reference_forward_on_a_mixed_batch():
             os.environ.pop("CUDA_VISIBLE_DEVICES", None)
         else:
             os.environ["CUDA_VISIBLE_DEVICES"] = env_before
+
+
+def test_fastdiv_header_matches_integer_division(tmp_path):
+    """speinet_b200/csrc/fastdiv.h (multiply-high division used by the rescoring kernels) against `/`: every divisor class the
+    kernels use (1, powers of two, image widths, grid sizes, 2^31 - 1), dividends up to 2^31 - 1 incl. all multiples' borders."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "fastdiv_check.cpp")
+    exe = str(tmp_path / "fastdiv_check")
+    subprocess.run([gxx, "-O2", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip() == "bad 0", res.stdout + res.stderr
