@@ -39,7 +39,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "speinet_b200.h")]
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(PKG, "..", "include", "speinet_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
